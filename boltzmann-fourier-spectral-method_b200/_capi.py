@@ -1,0 +1,81 @@
+"""ctypes binding of include/bfsm_b200.h (the C ABI of the CUDA library).
+
+There is no fallback: if the shared library is missing, `load()` raises.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libbfsm_b200.so")
+
+BFSM_OK, BFSM_ERR_INVALID, BFSM_ERR_UNSUPPORTED, BFSM_ERR_CUDA, BFSM_ERR_NOMEM = range(5)
+BFSM_FLAG_NO_FOLD = 1
+
+#: every symbol include/bfsm_b200.h declares
+EXPORTS = (
+    "bfsm_version", "bfsm_last_error", "bfsm_plan_create", "bfsm_plan_destroy", "bfsm_collide",
+    "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
+    "bfsm_plan_set_chunk",
+)
+
+
+class PlanInfo(ctypes.Structure):
+    _fields_ = [
+        ("n", ctypes.c_int), ("n_r", ctypes.c_int), ("n_s", ctypes.c_int),
+        ("folded", ctypes.c_int), ("pairs_total", ctypes.c_int), ("pairs_local", ctypes.c_int),
+        ("chunk_pairs", ctypes.c_int), ("launches_per_cell", ctypes.c_int),
+        ("scratch_bytes", ctypes.c_longlong),
+    ]
+
+
+class BfsmError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"bfsm error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """Load csrc/libbfsm_b200.so and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA extension is mandatory; there is no CPU fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    dp = ctypes.POINTER(ctypes.c_double)
+    vp = ctypes.c_void_p
+    lib.bfsm_version.restype = ctypes.c_int
+    lib.bfsm_last_error.restype = ctypes.c_char_p
+    lib.bfsm_plan_create.restype = ctypes.c_int
+    lib.bfsm_plan_create.argtypes = [
+        ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        ctypes.c_int, dp, dp, ctypes.c_int, dp, dp, dp, dp,
+        ctypes.c_double, ctypes.c_double, ctypes.c_double,
+        ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+    lib.bfsm_plan_destroy.restype = ctypes.c_int
+    lib.bfsm_plan_destroy.argtypes = [vp]
+    lib.bfsm_collide.restype = ctypes.c_int
+    lib.bfsm_collide.argtypes = [vp, vp, vp, ctypes.c_int, vp]
+    lib.bfsm_collide_host.restype = ctypes.c_int
+    lib.bfsm_collide_host.argtypes = [vp, vp, vp, ctypes.c_int, vp]
+    lib.bfsm_gain_hat.restype = ctypes.c_int
+    lib.bfsm_gain_hat.argtypes = [vp, vp, vp, vp]
+    lib.bfsm_finish.restype = ctypes.c_int
+    lib.bfsm_finish.argtypes = [vp, vp, vp, vp, vp]
+    lib.bfsm_plan_get_info.restype = ctypes.c_int
+    lib.bfsm_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfo)]
+    lib.bfsm_plan_set_chunk.restype = ctypes.c_int
+    lib.bfsm_plan_set_chunk.argtypes = [vp, ctypes.c_int]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != BFSM_OK:
+        msg = load().bfsm_last_error()
+        raise BfsmError(rc, msg.decode() if msg else "")

@@ -1,0 +1,540 @@
+// bfsm_capi.cu -- plan management, host-side table construction and kernel launches behind
+// the C ABI declared in include/bfsm_b200.h.  No torch types, no cuFFT, no CPU fallback.
+#include "../../include/bfsm_b200.h"
+#include "bfsm_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace bfsm;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            char buf_[512];                                                                   \
+            snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                     \
+            return fail(BFSM_ERR_CUDA, buf_);                                                 \
+        }                                                                                     \
+    } while (0)
+
+const long double PI_L = 3.14159265358979323846264338327950288L;
+const double PI_D = 3.14159265358979323846; // Utilities/constants.hpp:7
+
+// FFTWBoltzmannOperator.hpp:17-21
+double sincc(double x)
+{
+    const double eps = 2.220446049250313e-16;
+    return std::sin(x + eps) / (x + eps);
+}
+
+struct DeviceBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+} // namespace
+
+struct bfsm_plan {
+    int N = 0, n_r = 0, n_s = 0, device = 0;
+    double gamma = 0, b_gamma = 0, L = 0;
+    int folded = 0;
+    int pairs_total = 0, pairs_local = 0;
+    int n_r_local = 0;
+    int M = 0; // |l|^2 table length
+    int chunk = 0;
+    int gy = 1;       // CTAs per plane in k_plane_gain
+    int G = 1;        // cross-CTA pair groups in k_pencil_gain (= number of S partials)
+    int sm_count = 148;
+    int shard_index = 0, shard_count = 1;
+    long long scratch_bytes = 0;
+
+    // device tables
+    cplx *tw = nullptr;       // [N] exp(+2 pi i t/N)
+    cplx *phase = nullptr;    // [pairs_local][3][N]
+    int *pair_r = nullptr;    // [pairs_local] local radius index
+    double *pair_w = nullptr; // [pairs_local] spherical weight (x2 when folded)
+    int *r_end = nullptr;     // [n_r_local] one past the last local pair of that radius
+    double *coef = nullptr;   // [n_r_local][M]
+    double *beta2 = nullptr;  // [M]
+    // device scratch
+    cplx *fhat = nullptr;  // [N^3]
+    cplx *tmp = nullptr;   // [max(2, n_r_local)][N^3]  hybrid scratch of the single-shot stages
+    cplx *hyb = nullptr;   // [2*chunk][N^3]
+    double *S = nullptr;   // [G][n_r_local][N^3]
+    cplx *qhat = nullptr;  // [N^3]
+    double *stage_f = nullptr, *stage_q = nullptr; // host-pointer entry point staging
+    size_t stage_cells = 0;
+    std::vector<void *> allocs;
+};
+
+namespace {
+
+int dev_alloc(bfsm_plan *p, void **out, size_t bytes)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+    if (e != cudaSuccess) {
+        char b[256];
+        snprintf(b, sizeof b, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        return fail(e == cudaErrorMemoryAllocation ? BFSM_ERR_NOMEM : BFSM_ERR_CUDA, b);
+    }
+    p->allocs.push_back(q);
+    p->scratch_bytes += (long long)bytes;
+    *out = q;
+    return BFSM_OK;
+}
+
+template <class T> int upload(bfsm_plan *p, T **out, const std::vector<T> &h)
+{
+    int rc = dev_alloc(p, (void **)out, h.size() * sizeof(T));
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return BFSM_OK;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = std::getenv(name);
+    if (!s || !*s) return dflt;
+    return std::atoi(s);
+}
+
+// ---- per-N launch geometry ------------------------------------------------------------
+template <int N> struct Launch;
+template <> struct Launch<64> { static constexpr int TG = 256, GROUPS = 2, MINB = 1, PG = 4, G = 1, CHUNK = 8; };
+template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, G = 4, CHUNK = 64; };
+template <> struct Launch<16> { static constexpr int TG = 64, GROUPS = 2, MINB = 4, PG = 8, G = 8, CHUNK = 256; };
+
+template <int N> size_t plane_gain_smem()
+{
+    using Lc = Launch<N>;
+    return sizeof(cplx) * ((size_t)N * N + (size_t)Lc::GROUPS * N * Geo<N>::ROW +
+                           (size_t)Lc::GROUPS * 2 * 3 * N);
+}
+template <int N> size_t plane_smem() { return sizeof(cplx) * (size_t)N * Geo<N>::ROW; }
+template <int N> size_t pencil_gain_smem()
+{
+    return sizeof(cplx) * (size_t)Launch<N>::PG * 2 * N * TZ;
+}
+
+template <int N> int configure_kernels()
+{
+    using Lc = Launch<N>;
+    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)plane_gain_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pencil_gain_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_plane<N, -1, PLANE_REAL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_plane<N, +1, PLANE_FINAL>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem<N>()));
+    return BFSM_OK;
+}
+
+// ---- one evaluation, split in the two halves the multi-GPU path needs -------------------
+
+// f -> fhat (scaled by 1/N^3) -> partial gain spectrum of this shard
+template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f, cudaStream_t st)
+{
+    using Lc = Launch<N>;
+    constexpr size_t N3 = (size_t)N * N * N;
+    constexpr int TILES = N * N / TZ;
+    constexpr int TGP = Geo<N>::B * TZ;
+
+    // forward transform of f (cpp:168-186)
+    k_plane<N, -1, PLANE_REAL><<<dim3(N, 1), N * Geo<N>::B, plane_smem<N>(), st>>>(
+        f, 1, 0, nullptr, nullptr, nullptr, p->tw, p->tmp);
+    k_pencil_fwd<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, 1.0 / (double)N3, p->fhat);
+
+    // gain: S_r = sum_sigma w Re(g1 g2)
+    CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)p->G * p->n_r_local * N3, st));
+    for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk) {
+        const int nc = std::min(p->chunk, p->pairs_local - c0);
+        const int items = 2 * nc;
+        int gy = std::min(p->gy, (items + Lc::GROUPS - 1) / Lc::GROUPS);
+        if (gy < 1) gy = 1;
+        k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
+            <<<dim3(N, gy), Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
+                p->fhat, p->phase, p->tw, p->hyb, c0, items);
+        const int G = std::min(p->G, nc);
+        k_pencil_gain<N, Lc::PG><<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
+            p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+    }
+
+    // Qhat = sum_r coef_r(|l|^2) FFT3(S_r)   (cpp:249-273)
+    if (p->n_r_local > 0) {
+        k_plane<N, -1, PLANE_REAL><<<dim3(N, p->n_r_local), N * Geo<N>::B, plane_smem<N>(), st>>>(
+            p->S, p->G, (size_t)p->n_r_local * N3, nullptr, nullptr, nullptr, p->tw, p->tmp);
+    }
+    k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
+    CUDA_TRY(cudaGetLastError());
+    return BFSM_OK;
+}
+
+// loss term + inverse transform + combine (cpp:281-330); needs p->fhat of the same f
+template <int N> int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st)
+{
+    constexpr int TILES = N * N / TZ;
+    constexpr int TGP = Geo<N>::B * TZ;
+    k_plane<N, +1, PLANE_FINAL><<<dim3(N, 2), N * Geo<N>::B, plane_smem<N>(), st>>>(
+        nullptr, 0, 0, qhat, p->fhat, p->beta2, p->tw, p->tmp);
+    k_pencil_final<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, f, Q);
+    CUDA_TRY(cudaGetLastError());
+    return BFSM_OK;
+}
+
+template <int N> int launches_per_cell(const bfsm_plan *p)
+{
+    const int chunks = (p->pairs_local + p->chunk - 1) / p->chunk;
+    return 2 + 2 * chunks + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
+}
+
+#define DISPATCH_N(p, CALL)                                           \
+    switch ((p)->N) {                                                 \
+    case 16: { constexpr int N_ = 16; return CALL; }                  \
+    case 32: { constexpr int N_ = 32; return CALL; }                  \
+    case 64: { constexpr int N_ = 64; return CALL; }                  \
+    default: return fail(BFSM_ERR_UNSUPPORTED, "unsupported grid size"); \
+    }
+
+int do_gain_hat(bfsm_plan *p, cplx *qhat, const double *f, cudaStream_t st)
+{
+    DISPATCH_N(p, run_gain_hat<N_>(p, qhat, f, st));
+}
+int do_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st)
+{
+    DISPATCH_N(p, run_finish<N_>(p, Q, qhat, f, st));
+}
+int do_configure(bfsm_plan *p) { DISPATCH_N(p, configure_kernels<N_>()); }
+int do_launch_count(const bfsm_plan *p) { DISPATCH_N(p, launches_per_cell<N_>(p)); }
+
+struct GuardDevice {
+    int prev = -1;
+    bool ok = true;
+    explicit GuardDevice(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~GuardDevice()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+} // namespace
+
+// =========================================================================== C ABI
+
+extern "C" int bfsm_version(void) { return BFSM_VERSION; }
+
+extern "C" const char *bfsm_last_error(void) { return g_err.c_str(); }
+
+extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r,
+                                const double *rho, const double *w_r, int n_s, const double *sx,
+                                const double *sy, const double *sz, const double *w_s,
+                                double gamma, double b_gamma, double L, int device,
+                                int shard_index, int shard_count, unsigned flags)
+{
+    if (!out) return fail(BFSM_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!rho || !w_r || !sx || !sy || !sz || !w_s)
+        return fail(BFSM_ERR_INVALID, "quadrature pointer is NULL");
+    if (n_r <= 0 || n_s <= 0) return fail(BFSM_ERR_INVALID, "quadrature sizes must be positive");
+    if (nvx <= 0 || nvy <= 0 || nvz <= 0) return fail(BFSM_ERR_INVALID, "grid sizes must be positive");
+    if (!(L > 0.0)) return fail(BFSM_ERR_INVALID, "L must be positive");
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
+        return fail(BFSM_ERR_INVALID, "shard_index/shard_count out of range");
+    if (nvx != nvy || nvy != nvz || (nvx != 16 && nvx != 32 && nvx != 64)) {
+        char b[160];
+        snprintf(b, sizeof b, "grid %dx%dx%d not supported: this build handles cubic 16/32/64", nvx,
+                 nvy, nvz);
+        return fail(BFSM_ERR_UNSUPPORTED, b);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BFSM_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(BFSM_ERR_INVALID, "device ordinal out of range");
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+
+    bfsm_plan *p = new bfsm_plan;
+    p->N = nvx;
+    p->n_r = n_r;
+    p->n_s = n_s;
+    p->device = device;
+    p->gamma = gamma;
+    p->b_gamma = b_gamma;
+    p->L = L;
+    p->shard_index = shard_index;
+    p->shard_count = shard_count;
+    const int N = p->N;
+    const size_t N3 = (size_t)N * N * N;
+
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+
+    // ---- antipodal folding: partner[s] = index of -sigma_s with equal weight, or -1
+    std::vector<int> rep; // directions actually transformed
+    std::vector<double> rep_w;
+    {
+        std::vector<int> partner(n_s, -1);
+        bool all = !(flags & BFSM_FLAG_NO_FOLD) && (n_s % 2 == 0);
+        if (all) {
+            for (int s = 0; s < n_s && all; ++s) {
+                if (partner[s] >= 0) continue;
+                int found = -1;
+                for (int t = 0; t < n_s; ++t) {
+                    if (t == s || partner[t] >= 0) continue;
+                    if (sx[t] == -sx[s] && sy[t] == -sy[s] && sz[t] == -sz[s] && w_s[t] == w_s[s]) {
+                        found = t;
+                        break;
+                    }
+                }
+                if (found < 0) {
+                    all = false;
+                } else {
+                    partner[s] = found;
+                    partner[found] = s;
+                }
+            }
+        }
+        p->folded = all ? 1 : 0;
+        for (int s = 0; s < n_s; ++s) {
+            if (p->folded) {
+                if (partner[s] > s) { // keep the lower index of each antipodal couple
+                    rep.push_back(s);
+                    rep_w.push_back(2.0 * w_s[s]);
+                }
+            } else {
+                rep.push_back(s);
+                rep_w.push_back(w_s[s]);
+            }
+        }
+    }
+    const int n_dir = (int)rep.size();
+    p->pairs_total = n_r * n_dir;
+    const int lo = (int)(((long long)p->pairs_total * shard_index) / shard_count);
+    const int hi = (int)(((long long)p->pairs_total * (shard_index + 1)) / shard_count);
+    p->pairs_local = hi - lo;
+
+    // ---- per-pair tables (work list is r-major: pair = r*n_dir + d)
+    const int r_first = (p->pairs_local > 0) ? lo / n_dir : 0;
+    const int r_last = (p->pairs_local > 0) ? (hi - 1) / n_dir : -1;
+    p->n_r_local = r_last - r_first + 1;
+    std::vector<int> h_pair_r(std::max(p->pairs_local, 1));
+    std::vector<double> h_pair_w(std::max(p->pairs_local, 1));
+    std::vector<int> h_r_end(std::max(p->n_r_local, 1), 0);
+    std::vector<cplx> h_phase((size_t)std::max(p->pairs_local, 1) * 3 * N);
+    std::vector<int> mode(N);
+    for (int t = 0; t < N; ++t) mode[t] = t < N / 2 ? t : t - N; // cpp:50-57
+    for (int q = 0; q < p->pairs_local; ++q) {
+        const int pair = lo + q;
+        const int r = pair / n_dir, d = pair % n_dir, s = rep[d];
+        h_pair_r[q] = r - r_first;
+        h_pair_w[q] = rep_w[d];
+        h_r_end[r - r_first] = q + 1;
+        // theta = -(pi/(2L)) * rho_r * (l . sigma)  (cpp:209-210), separable in the three axes
+        const long double c = -(PI_L / (2.0L * (long double)L)) * (long double)rho[r];
+        const double sig[3] = {sx[s], sy[s], sz[s]};
+        for (int ax = 0; ax < 3; ++ax)
+            for (int t = 0; t < N; ++t) {
+                const long double th = c * (long double)mode[t] * (long double)sig[ax];
+                h_phase[((size_t)q * 3 + ax) * N + t] = make_double2((double)cosl(th), (double)sinl(th));
+            }
+    }
+
+    // ---- beta1 / beta2 tables indexed by the integer |l|^2 (cpp:252-265, 281-299)
+    p->M = 3 * (N / 2) * (N / 2) + 1;
+    const double fft_scale = 1.0 / (double)N3; // cpp:162
+    std::vector<double> h_coef((size_t)std::max(p->n_r_local, 1) * p->M, 0.0);
+    std::vector<double> h_beta2(p->M, 0.0);
+    for (int m = 0; m < p->M; ++m) {
+        const double norm_l = std::sqrt((double)m);
+        for (int rl = 0; rl < p->n_r_local; ++rl) {
+            const int r = r_first + rl;
+            const double beta1 = 4 * PI_D * b_gamma * sincc(PI_D * rho[r] * norm_l / (2 * L));
+            h_coef[(size_t)rl * p->M + m] = fft_scale * w_r[r] * std::pow(rho[r], gamma + 2) * beta1;
+        }
+        double b2 = 0.0;
+        for (int r = 0; r < n_r; ++r)
+            b2 += 16 * PI_D * PI_D * b_gamma * w_r[r] * std::pow(rho[r], gamma + 2) *
+                  sincc(PI_D * rho[r] * norm_l / L);
+        h_beta2[m] = b2; // fft_scale is already folded into fhat
+    }
+    std::vector<cplx> h_tw(N);
+    for (int t = 0; t < N; ++t) {
+        const long double a = 2.0L * PI_L * (long double)t / (long double)N;
+        h_tw[t] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+
+    // ---- launch geometry
+    int dflt_chunk = (N == 64) ? Launch<64>::CHUNK : (N == 32) ? Launch<32>::CHUNK : Launch<16>::CHUNK;
+    p->chunk = std::max(1, env_int("BFSM_CHUNK_PAIRS", dflt_chunk));
+    p->chunk = std::min(p->chunk, std::max(1, p->pairs_local));
+    p->G = (N == 64) ? Launch<64>::G : (N == 32) ? Launch<32>::G : Launch<16>::G;
+    {
+        const int occ = (N == 64) ? 1 : (N == 32) ? 3 : 8;
+        int gy = (p->sm_count * occ) / N;
+        p->gy = std::max(1, env_int("BFSM_GAIN_GY", std::max(1, gy)));
+    }
+
+    int rc = BFSM_OK;
+    auto bail = [&](int code) {
+        std::string keep = g_err;
+        bfsm_plan_destroy(p);
+        g_err = keep;
+        return code;
+    };
+    if ((rc = upload(p, &p->tw, h_tw))) return bail(rc);
+    if ((rc = upload(p, &p->phase, h_phase))) return bail(rc);
+    if ((rc = upload(p, &p->pair_r, h_pair_r))) return bail(rc);
+    if ((rc = upload(p, &p->pair_w, h_pair_w))) return bail(rc);
+    if ((rc = upload(p, &p->r_end, h_r_end))) return bail(rc);
+    if ((rc = upload(p, &p->coef, h_coef))) return bail(rc);
+    if ((rc = upload(p, &p->beta2, h_beta2))) return bail(rc);
+    if ((rc = dev_alloc(p, (void **)&p->fhat, sizeof(cplx) * N3))) return bail(rc);
+    if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bail(rc);
+    if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
+        return bail(rc);
+    if ((rc = dev_alloc(p, (void **)&p->hyb, sizeof(cplx) * N3 * 2 * (size_t)p->chunk))) return bail(rc);
+    if ((rc = dev_alloc(p, (void **)&p->S,
+                        sizeof(double) * N3 * (size_t)p->G * std::max(1, p->n_r_local))))
+        return bail(rc);
+    if ((rc = do_configure(p))) return bail(rc);
+    *out = p;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_plan_destroy(bfsm_plan *p)
+{
+    if (!p) return BFSM_OK;
+    GuardDevice guard(p->device);
+    for (void *q : p->allocs) cudaFree(q);
+    if (p->stage_f) cudaFree(p->stage_f);
+    if (p->stage_q) cudaFree(p->stage_q);
+    delete p;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
+{
+    if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
+    GuardDevice guard(p->device);
+    const int N = p->N;
+    const size_t N3 = (size_t)N * N * N;
+    int dflt = (N == 64) ? Launch<64>::CHUNK : (N == 32) ? Launch<32>::CHUNK : Launch<16>::CHUNK;
+    int c = chunk_pairs > 0 ? chunk_pairs : dflt;
+    c = std::min(c, std::max(1, p->pairs_local));
+    if (c > p->chunk) {
+        // grow the hybrid scratch
+        cplx *q = nullptr;
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMalloc((void **)&q, sizeof(cplx) * N3 * 2 * (size_t)c));
+        for (auto &a : p->allocs)
+            if (a == (void *)p->hyb) a = q;
+        cudaFree(p->hyb);
+        p->scratch_bytes += (long long)(sizeof(cplx) * N3 * 2 * (size_t)(c - p->chunk));
+        p->hyb = q;
+    }
+    p->chunk = c;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
+{
+    if (!p || !info) return fail(BFSM_ERR_INVALID, "NULL argument");
+    info->n = p->N;
+    info->n_r = p->n_r;
+    info->n_s = p->n_s;
+    info->folded = p->folded;
+    info->pairs_total = p->pairs_total;
+    info->pairs_local = p->pairs_local;
+    info->chunk_pairs = p->chunk;
+    info->launches_per_cell = do_launch_count(p);
+    info->scratch_bytes = p->scratch_bytes;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_gain_hat(bfsm_plan *p, double *Qhat_dev, const double *f_dev, void *stream)
+{
+    if (!p || !Qhat_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    GuardDevice guard(p->device);
+    return do_gain_hat(p, reinterpret_cast<cplx *>(Qhat_dev), f_dev, (cudaStream_t)stream);
+}
+
+extern "C" int bfsm_finish(bfsm_plan *p, double *Q_dev, const double *Qhat_dev, const double *f_dev,
+                           void *stream)
+{
+    if (!p || !Q_dev || !Qhat_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    GuardDevice guard(p->device);
+    return do_finish(p, Q_dev, reinterpret_cast<const cplx *>(Qhat_dev), f_dev, (cudaStream_t)stream);
+}
+
+extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, int n_cells, void *stream)
+{
+    if (!p || !Q_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    if (n_cells < 0) return fail(BFSM_ERR_INVALID, "n_cells must be >= 0");
+    if (p->shard_count != 1)
+        return fail(BFSM_ERR_INVALID,
+                    "bfsm_collide needs an unsharded plan; use bfsm_gain_hat + all-reduce + bfsm_finish");
+    GuardDevice guard(p->device);
+    const size_t N3 = (size_t)p->N * p->N * p->N;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int c = 0; c < n_cells; ++c) {
+        int rc = do_gain_hat(p, p->qhat, f_dev + (size_t)c * N3, st);
+        if (rc) return rc;
+        rc = do_finish(p, Q_dev + (size_t)c * N3, p->qhat, f_dev + (size_t)c * N3, st);
+        if (rc) return rc;
+    }
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_collide_host(bfsm_plan *p, double *Q_host, const double *f_host, int n_cells,
+                                 void *stream)
+{
+    if (!p || !Q_host || !f_host) return fail(BFSM_ERR_INVALID, "NULL argument");
+    if (n_cells < 0) return fail(BFSM_ERR_INVALID, "n_cells must be >= 0");
+    if (n_cells == 0) return BFSM_OK;
+    GuardDevice guard(p->device);
+    const size_t N3 = (size_t)p->N * p->N * p->N;
+    const size_t bytes = sizeof(double) * N3 * (size_t)n_cells;
+    if (p->stage_cells < (size_t)n_cells) {
+        if (p->stage_f) cudaFree(p->stage_f);
+        if (p->stage_q) cudaFree(p->stage_q);
+        p->stage_f = p->stage_q = nullptr;
+        p->stage_cells = 0;
+        CUDA_TRY(cudaMalloc((void **)&p->stage_f, bytes));
+        CUDA_TRY(cudaMalloc((void **)&p->stage_q, bytes));
+        p->stage_cells = (size_t)n_cells;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(p->stage_f, f_host, bytes, cudaMemcpyHostToDevice, st));
+    int rc = bfsm_collide(p, p->stage_q, p->stage_f, n_cells, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(Q_host, p->stage_q, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return BFSM_OK;
+}

@@ -1,0 +1,229 @@
+// bfsm_fft.cuh -- fp64 FFT building blocks for the sm_100a collision kernels.
+//
+// A length-N line (N = A*B) is transformed in place in shared memory by two
+// register-radix passes (decimation in frequency):
+//   pass 1, one unit per column b:   v[a] = x[B*a + b]  -> radix-A DFT -> * W_N^(b*k1)
+//                                     -> stored at position B*k1 + b
+//   pass 2, one unit per k1:          v[b] = pos[B*k1+b] -> radix-B DFT
+//                                     -> X[k1 + A*k2] left at position B*k1 + k2
+// so natural frequency k = k1 + A*k2 lives at position B*k1 + k2.  A (y,z) plane is an
+// N x ROW array of complex doubles, position p of a row at column p + (p>>3)
+// (one pad slot per 8 elements) and ROW chosen so that both the row-wise and the
+// column-wise passes are free of shared-memory bank conflicts for 16-byte accesses.
+//
+// No cuFFT, no tensor cores: the whole path is fp64 SIMT (DFMA/DADD) + LDS/STS.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace bfsm {
+
+typedef double2 cplx;
+
+template <int N> struct Geo;
+template <> struct Geo<64> { static constexpr int A = 8, B = 8, ROW = 73; };
+template <> struct Geo<32> { static constexpr int A = 8, B = 4, ROW = 42; };
+template <> struct Geo<16> { static constexpr int A = 4, B = 4, ROW = 18; };
+
+__device__ __forceinline__ int padk(int k) { return k + (k >> 3); }
+
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cmul(cplx a, cplx b)
+{
+    return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// a * conj(b)
+__device__ __forceinline__ cplx cmulc(cplx a, cplx b)
+{
+    return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// multiply by SIGN*i
+template <int SIGN> __device__ __forceinline__ cplx mul_si(cplx a)
+{
+    return SIGN > 0 ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x);
+}
+
+// Natural-order in-place DFTs with kernel exp(SIGN * 2 pi i n k / R).
+template <int SIGN> __device__ __forceinline__ void dft4(cplx &x0, cplx &x1, cplx &x2, cplx &x3)
+{
+    const cplx c0 = cadd(x0, x2), c1 = csub(x0, x2);
+    const cplx c2 = cadd(x1, x3), c3 = mul_si<SIGN>(csub(x1, x3));
+    x0 = cadd(c0, c2);
+    x2 = csub(c0, c2);
+    x1 = cadd(c1, c3);
+    x3 = csub(c1, c3);
+}
+
+template <int R, int SIGN> struct Dft;
+
+template <int SIGN> struct Dft<4, SIGN> {
+    static __device__ __forceinline__ void run(cplx (&v)[4]) { dft4<SIGN>(v[0], v[1], v[2], v[3]); }
+};
+
+template <int SIGN> struct Dft<8, SIGN> {
+    static __device__ __forceinline__ void run(cplx (&v)[8])
+    {
+        constexpr double h = 0.70710678118654752440;
+        constexpr double s = (double)SIGN;
+        cplx a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+        cplx a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+        cplx a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
+        cplx a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+        // odd half times W8^n, W8 = exp(SIGN*i*pi/4)
+        a5 = make_double2((a5.x - s * a5.y) * h, (a5.y + s * a5.x) * h);
+        a6 = mul_si<SIGN>(a6);
+        a7 = make_double2((-a7.x - s * a7.y) * h, (-a7.y + s * a7.x) * h);
+        dft4<SIGN>(a0, a1, a2, a3); // X[0], X[2], X[4], X[6]
+        dft4<SIGN>(a4, a5, a6, a7); // X[1], X[3], X[5], X[7]
+        v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+        v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
+    }
+};
+
+// Pass-1 twiddles of the calling thread: tw[k1-1] = W_N^(SIGN*b*k1), k1 = 1..A-1.
+// twtab[t] = exp(+2 pi i t / N), t in [0,N), tabulated on the host in long double.
+template <int N, int SIGN>
+__device__ __forceinline__ void load_twiddles(cplx (&tw)[Geo<N>::A - 1], const cplx *__restrict__ twtab,
+                                              int b)
+{
+#pragma unroll
+    for (int k1 = 1; k1 < Geo<N>::A; ++k1) {
+        const cplx w = __ldg(&twtab[(b * k1) & (N - 1)]);
+        tw[k1 - 1] = make_double2(w.x, SIGN > 0 ? w.y : -w.y);
+    }
+}
+
+// ------------------------------------------------------------------ plane (y,z) passes
+// `buf` is an N x ROW padded plane in shared memory, `tg` the thread's index inside
+// its group of TG threads.  TG must be a multiple of B so that a thread's column
+// residue b = tg % B is the same for every unit it owns (twiddles live in registers).
+
+// z pass 1: `in(j,k)` supplies element (row j, spectral/physical column k).
+template <int N, int SIGN, int TG, class In>
+__device__ __forceinline__ void z1_pass(cplx *buf, const cplx (&tw)[Geo<N>::A - 1], int tg, In in)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
+    static_assert(TG % B == 0, "TG must be a multiple of B");
+#pragma unroll
+    for (int u0 = 0; u0 < N * B; u0 += TG) {
+        const int u = u0 + tg;
+        if ((N * B) % TG != 0 && u >= N * B) break;
+        const int j = u / B, b = u % B;
+        cplx v[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) v[a] = in(j, B * a + b);
+        Dft<A, SIGN>::run(v);
+        cplx *row = buf + j * ROW;
+        row[padk(b)] = v[0];
+#pragma unroll
+        for (int k1 = 1; k1 < A; ++k1) row[padk(B * k1 + b)] = cmul(v[k1], tw[k1 - 1]);
+    }
+}
+
+// z pass 2 (in place).
+template <int N, int SIGN, int TG> __device__ __forceinline__ void z2_pass(cplx *buf, int tg)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
+#pragma unroll
+    for (int u0 = 0; u0 < N * A; u0 += TG) {
+        const int u = u0 + tg;
+        if ((N * A) % TG != 0 && u >= N * A) break;
+        const int j = u / A, k1 = u % A;
+        cplx *row = buf + j * ROW;
+        cplx v[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) v[b] = row[padk(B * k1 + b)];
+        Dft<B, SIGN>::run(v);
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) row[padk(B * k1 + k2)] = v[k2];
+    }
+}
+
+// y pass 1 (in place); unit = (column position q, row residue b) with b = u % B so the
+// twiddles are the same registers as in z pass 1.
+template <int N, int SIGN, int TG>
+__device__ __forceinline__ void y1_pass(cplx *buf, const cplx (&tw)[Geo<N>::A - 1], int tg)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
+#pragma unroll
+    for (int u0 = 0; u0 < N * B; u0 += TG) {
+        const int u = u0 + tg;
+        if ((N * B) % TG != 0 && u >= N * B) break;
+        const int b = u % B, q = u / B;
+        cplx *col = buf + padk(q);
+        cplx v[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) v[a] = col[(B * a + b) * ROW];
+        Dft<A, SIGN>::run(v);
+        col[b * ROW] = v[0];
+#pragma unroll
+        for (int k1 = 1; k1 < A; ++k1) col[(B * k1 + b) * ROW] = cmul(v[k1], tw[k1 - 1]);
+    }
+}
+
+// y pass 2: results leave shared memory through `out(y, z, value)` in natural order;
+// consecutive threads own consecutive natural z, so global stores coalesce.
+template <int N, int SIGN, int TG, class Out>
+__device__ __forceinline__ void y2_pass(const cplx *buf, int tg, Out out)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
+#pragma unroll
+    for (int u0 = 0; u0 < N * A; u0 += TG) {
+        const int u = u0 + tg;
+        if ((N * A) % TG != 0 && u >= N * A) break;
+        const int z = u % N, k1 = u / N;
+        const int q = B * (z % A) + z / A; // position holding natural index z
+        const cplx *col = buf + padk(q);
+        cplx v[B];
+#pragma unroll
+        for (int b = 0; b < B; ++b) v[b] = col[(B * k1 + b) * ROW];
+        Dft<B, SIGN>::run(v);
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) out(k1 + A * k2, z, v[k2]);
+    }
+}
+
+// ------------------------------------------------------------------ x pencil passes
+// A tile is N x TZ (x by 8 consecutive z) complex doubles, dense in shared memory;
+// TGP = B*TZ threads, thread (b = tg / TZ, z = tg % TZ) in pass 1.
+constexpr int TZ = 8;
+
+template <int N, int SIGN, class In>
+__device__ __forceinline__ void x1_pass(cplx *sm, const cplx (&tw)[Geo<N>::A - 1], int tg, In in)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B;
+    const int z = tg % TZ, b = tg / TZ;
+    cplx v[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) v[a] = in(B * a + b, z);
+    Dft<A, SIGN>::run(v);
+    sm[b * TZ + z] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < A; ++k1) sm[(B * k1 + b) * TZ + z] = cmul(v[k1], tw[k1 - 1]);
+}
+
+// Number of pass-2 units a thread of a B*TZ group owns.
+template <int N> struct X2 { static constexpr int UNITS = Geo<N>::A / Geo<N>::B; };
+
+// x pass 2, unit m of the thread: fills v[k2] = X[k1 + A*k2]; returns k1.
+template <int N, int SIGN>
+__device__ __forceinline__ int x2_unit(const cplx *sm, int tg, int m, cplx (&v)[Geo<N>::B])
+{
+    constexpr int B = Geo<N>::B;
+    const int u = tg + m * (B * TZ);
+    const int z = u % TZ, k1 = u / TZ;
+#pragma unroll
+    for (int b = 0; b < B; ++b) v[b] = sm[(B * k1 + b) * TZ + z];
+    Dft<B, SIGN>::run(v);
+    return k1;
+}
+
+// Fourier mode of index t (FFTWBoltzmannOperator.cpp:50-57): 0..N/2-1, -N/2..-1.
+template <int N> __device__ __forceinline__ int mode_of(int t) { return t < N / 2 ? t : t - N; }
+
+__device__ __forceinline__ void group_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+} // namespace bfsm

@@ -1,0 +1,364 @@
+// bfsm_kernels.cuh -- the sm_100a kernels of the fused FFT-collision path.
+//
+// One evaluation Q(f,f) on an N^3 grid (reference: FFTWBoltzmannOperator.cpp:147-334):
+//
+//   f --k_plane<REAL>--> Fh --k_pencil_fwd--> fhat/N^3                     (cpp:168-186)
+//   for chunks of (r,sigma) pairs:                                          (cpp:191-250)
+//       k_plane_gain : fhat plane x separable phase -> 2-D inverse FFT (y,z) of both
+//                      alpha1*fhat and conj(alpha1)*fhat -> hybrid scratch (L2 resident)
+//       k_pencil_gain: inverse FFT along x of both, Re(g1*g2) * w_pair accumulated in
+//                      registers over the chunk's pairs, per-r flush into S_r
+//   S_r --k_plane<REAL>--> Ph_r --k_pencil_accum--> Qhat = sum_r coef_r(|l|^2) FFT3(S_r)
+//                                                                           (cpp:249-273)
+//   Qhat, beta2*fhat --k_plane<FINAL>--> H --k_pencil_final--> Q = Re(Qg) - Re(h) f
+//                                                                           (cpp:281-330)
+//
+// Differences from the reference's loop nest, all exact up to fp64 rounding:
+//   * the forward transform is linear, so it is applied once per radius r to
+//     S_r = sum_sigma w_sigma Re(g1 g2) instead of once per pair (3P+4 -> 2P+N_r+4 FFTs);
+//   * beta1 is real and even in l, so only Re(g1 g2) can reach Re(Q_gain) (the only part
+//     the reference keeps, cpp:326);
+//   * exp(i theta(l)) = ex[i] ey[j] ez[k] (theta is linear in l): three N-entry tables per pair;
+//   * beta1(r,|l|) and beta2(|l|) depend on l only through the integer |l|^2: tabulated;
+//   * 1/N^3 (a power of two, hence exact) is folded into fhat and the tables.
+#pragma once
+#include "bfsm_fft.cuh"
+
+namespace bfsm {
+
+// ---------------------------------------------------------------------------------------
+// k_plane_gain: grid (N planes, Gy), block GROUPS*TG.  Work item `it` of plane i is
+// (pair pl = it/2, array it&1); group g of CTA y owns items (y*GROUPS+g) + m*Gy*GROUPS.
+// Shared memory: fhat plane (N*N) | GROUPS padded planes (N*ROW) | GROUPS x 2 phase slots (3N).
+// ---------------------------------------------------------------------------------------
+template <int N, int TG, int GROUPS, int MINB>
+__global__ void __launch_bounds__(TG *GROUPS, MINB)
+k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
+             const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
+    constexpr int N3 = N * N * N;
+    static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *fpl = reinterpret_cast<cplx *>(smem_raw);
+    cplx *bufs = fpl + N * N;
+    cplx *phs = bufs + GROUPS * N * ROW;
+
+    const int i = blockIdx.x;
+    const int g = threadIdx.x / TG, tg = threadIdx.x % TG;
+    cplx *buf = bufs + g * N * ROW;
+    cplx *myph = phs + g * 2 * 3 * N;
+
+    for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = fhat[(size_t)i * N * N + t];
+
+    cplx tw[A - 1];
+    load_twiddles<N, +1>(tw, twtab, tg % B);
+
+    const int stride = gridDim.y * GROUPS;
+    const int first = blockIdx.y * GROUPS + g;
+    if (first < n_items && tg < 3 * N)
+        myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> 1)) * 3 * N + tg]);
+    __syncthreads();
+
+    int slot = 0;
+    for (int it = first; it < n_items; it += stride, slot ^= 1) {
+        const int arr = it & 1;
+        const cplx *P = myph + slot * 3 * N;
+        const bool have_next = (it + stride < n_items) && (tg < 3 * N);
+        cplx nxt = make_double2(0.0, 0.0);
+        if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + stride) >> 1)) * 3 * N + tg]);
+        const cplx exi = P[i];
+
+        // z pass 1 with the phase-weighted load fused in (cpp:198-225):
+        // A1 = e^{i theta} fhat, A2 = e^{-i theta} fhat, theta separable in (i,j,k).
+#pragma unroll
+        for (int u0 = 0; u0 < N * B; u0 += TG) {
+            const int u = u0 + tg;
+            const int j = u / B, b = u % B;
+            const cplx exy = cmul(exi, P[N + j]);
+            cplx v[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const int k = B * a + b;
+                const cplx e = cmul(exy, P[2 * N + k]);
+                const cplx f = fpl[j * N + k];
+                v[a] = arr ? cmulc(f, e) : cmul(f, e);
+            }
+            Dft<A, +1>::run(v);
+            cplx *row = buf + j * ROW;
+            row[padk(b)] = v[0];
+#pragma unroll
+            for (int k1 = 1; k1 < A; ++k1) row[padk(B * k1 + b)] = cmul(v[k1], tw[k1 - 1]);
+        }
+        group_sync(1 + g, TG);
+        z2_pass<N, +1, TG>(buf, tg);
+        group_sync(1 + g, TG);
+        if (have_next) myph[(slot ^ 1) * 3 * N + tg] = nxt;
+        y1_pass<N, +1, TG>(buf, tw, tg);
+        group_sync(1 + g, TG);
+        cplx *dst = hyb + ((size_t)it * N + i) * N * N;
+        y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { dst[y * N + z] = val; });
+        group_sync(1 + g, TG);
+    }
+    (void)N3;
+}
+
+// ---------------------------------------------------------------------------------------
+// k_pencil_gain: grid (N*N/TZ tiles, G), block PG*(B*TZ).  CTA (tile, gy) owns chunk pairs
+// [lo,hi) = share gy of the chunk; its PG groups take them round-robin.  Each group:
+// inverse x-FFT of g1' and g2' pencils, acc += w * Re(g1 g2) (cpp:233-246 + linearity of
+// the forward FFT).  At every change of radius r the PG partial sums are reduced through
+// shared memory in fixed order and added to S[gy][r] -- no atomics, deterministic.
+// ---------------------------------------------------------------------------------------
+template <int N, int PG>
+__global__ void __launch_bounds__(PG *Geo<N>::B *TZ)
+k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
+              const int *__restrict__ pair_r, const double *__restrict__ pair_w,
+              const int *__restrict__ r_end, double *__restrict__ S, int pair0, int n_pairs_chunk,
+              int n_r_local)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B;
+    constexpr int TGP = B * TZ, UNITS = X2<N>::UNITS, TILE = N * TZ;
+    constexpr size_t N3 = (size_t)N * N * N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx(*sm)[2][TILE] = reinterpret_cast<cplx(*)[2][TILE]>(smem_raw); // [PG][2][TILE]
+
+    const int g = threadIdx.x / TGP, tg = threadIdx.x % TGP;
+    const int y = blockIdx.x / (N / TZ), zg = blockIdx.x % (N / TZ);
+    const int G = gridDim.y;
+    const int lo = (int)(((long long)n_pairs_chunk * blockIdx.y) / G);
+    const int hi = (int)(((long long)n_pairs_chunk * (blockIdx.y + 1)) / G);
+
+    cplx tw[A - 1];
+    load_twiddles<N, +1>(tw, twtab, tg / TZ);
+
+    double acc[UNITS][B];
+#pragma unroll
+    for (int m = 0; m < UNITS; ++m)
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) acc[m][k2] = 0.0;
+
+    const size_t tile_off = (size_t)y * N + zg * TZ;
+    int p = lo;
+    while (p < hi) {
+        const int r = pair_r[pair0 + p];
+        int seg_end = r_end[r] - pair0;
+        if (seg_end > hi) seg_end = hi;
+        for (int q = p + g; q < seg_end; q += PG) {
+            const cplx *g1 = hyb + (size_t)(2 * q) * N3 + tile_off;
+            const cplx *g2 = g1 + N3;
+            x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return g1[(size_t)x * N * N + z]; });
+            x1_pass<N, +1>(sm[g][1], tw, tg, [&](int x, int z) { return g2[(size_t)x * N * N + z]; });
+            group_sync(1 + g, TGP);
+            const double w = pair_w[pair0 + q];
+#pragma unroll
+            for (int m = 0; m < UNITS; ++m) {
+                cplx v0[B], v1[B];
+                x2_unit<N, +1>(sm[g][0], tg, m, v0);
+                x2_unit<N, +1>(sm[g][1], tg, m, v1);
+#pragma unroll
+                for (int k2 = 0; k2 < B; ++k2)
+                    acc[m][k2] += w * (v0[k2].x * v1[k2].x - v0[k2].y * v1[k2].y);
+            }
+            group_sync(1 + g, TGP);
+        }
+        // flush this radius: fixed-order reduction over the PG groups
+        __syncthreads();
+        double *red = reinterpret_cast<double *>(&sm[0][0][0]); // PG*TILE doubles <= smem size
+#pragma unroll
+        for (int m = 0; m < UNITS; ++m)
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) {
+                red[g * TILE + (tg + m * TGP) * B + k2] = acc[m][k2];
+                acc[m][k2] = 0.0;
+            }
+        __syncthreads();
+        double *Sr = S + ((size_t)blockIdx.y * n_r_local + r) * N3 + tile_off;
+        for (int e = threadIdx.x; e < TILE; e += PG * TGP) {
+            const int x = e / TZ, z = e % TZ;
+            const int k1 = x % A, k2 = x / A;
+            const int src = (k1 * TZ + z) * B + k2;
+            double s = 0.0;
+#pragma unroll
+            for (int gg = 0; gg < PG; ++gg) s += red[gg * TILE + src];
+            Sr[(size_t)x * N * N + z] += s;
+        }
+        __syncthreads();
+        p = seg_end;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Generic single-shot plane kernel: grid (N planes, n_items), block TG = N*B.
+//   PLANE_REAL : in = sum_{g<n_partials} src_real[g*partial_stride + item*N^3 + ...] (imag 0)
+//   PLANE_FINAL: item 0: in = Qhat;  item 1: in = beta2[|l|^2] * fhat   (cpp:281-299)
+// out: dst[item][plane][y][z] in natural order.
+// ---------------------------------------------------------------------------------------
+enum { PLANE_REAL = 0, PLANE_FINAL = 1 };
+
+template <int N, int SIGN, int MODE>
+__global__ void __launch_bounds__(N *Geo<N>::B)
+k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stride,
+        const cplx *__restrict__ qhat, const cplx *__restrict__ fhat,
+        const double *__restrict__ beta2, const cplx *__restrict__ twtab, cplx *__restrict__ dst)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, TG = N * B;
+    constexpr size_t N3 = (size_t)N * N * N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *buf = reinterpret_cast<cplx *>(smem_raw);
+    const int i = blockIdx.x, item = blockIdx.y, tg = threadIdx.x;
+
+    cplx tw[A - 1];
+    load_twiddles<N, SIGN>(tw, twtab, tg % B);
+
+    if (MODE == PLANE_REAL) {
+        const double *s = src_real + (size_t)item * N3 + (size_t)i * N * N;
+        z1_pass<N, SIGN, TG>(buf, tw, tg, [&](int j, int k) {
+            double v = 0.0;
+            for (int gq = 0; gq < n_partials; ++gq) v += s[(size_t)gq * partial_stride + j * N + k];
+            return make_double2(v, 0.0);
+        });
+    } else {
+        const size_t off = (size_t)i * N * N;
+        const int li = mode_of<N>(i);
+        if (item == 0) {
+            z1_pass<N, SIGN, TG>(buf, tw, tg, [&](int j, int k) { return qhat[off + j * N + k]; });
+        } else {
+            z1_pass<N, SIGN, TG>(buf, tw, tg, [&](int j, int k) {
+                const int lj = mode_of<N>(j), lk = mode_of<N>(k);
+                const double b2 = __ldg(&beta2[li * li + lj * lj + lk * lk]);
+                const cplx f = fhat[off + j * N + k];
+                return make_double2(b2 * f.x, b2 * f.y);
+            });
+        }
+    }
+    __syncthreads();
+    z2_pass<N, SIGN, TG>(buf, tg);
+    __syncthreads();
+    y1_pass<N, SIGN, TG>(buf, tw, tg);
+    __syncthreads();
+    cplx *d = dst + (size_t)item * N3 + (size_t)i * N * N;
+    y2_pass<N, SIGN, TG>(buf, tg, [&](int y, int z, cplx val) { d[y * N + z] = val; });
+}
+
+// ---------------------------------------------------------------------------------------
+// Single-shot pencil kernels: grid N*N/TZ tiles, block B*TZ.
+// ---------------------------------------------------------------------------------------
+
+// fhat[i][j][k] = scale * FFT_x(Fh[.][j][k])           (forward transform of f, cpp:186)
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::B *TZ)
+k_pencil_fwd(const cplx *__restrict__ Fh, const cplx *__restrict__ twtab, double scale,
+             cplx *__restrict__ fhat)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS;
+    __shared__ __align__(16) cplx sm[N * TZ];
+    const int tg = threadIdx.x;
+    const int j = blockIdx.x / (N / TZ), kg = blockIdx.x % (N / TZ);
+    const size_t off = (size_t)j * N + kg * TZ;
+    cplx tw[A - 1];
+    load_twiddles<N, -1>(tw, twtab, tg / TZ);
+    x1_pass<N, -1>(sm, tw, tg, [&](int x, int z) { return Fh[off + (size_t)x * N * N + z]; });
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < UNITS; ++m) {
+        cplx v[B];
+        const int k1 = x2_unit<N, -1>(sm, tg, m, v);
+        const int z = (tg + m * B * TZ) % TZ;
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) {
+            const int i = k1 + A * k2;
+            fhat[off + (size_t)i * N * N + z] = make_double2(v[k2].x * scale, v[k2].y * scale);
+        }
+    }
+}
+
+// Qhat[l] = sum_r coef[r][|l|^2] * FFT_x(Ph_r)[l]      (cpp:252-273, register reduction over r)
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::B *TZ)
+k_pencil_accum(const cplx *__restrict__ Ph, const cplx *__restrict__ twtab,
+               const double *__restrict__ coef, int n_r_local, int M, cplx *__restrict__ Qhat)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS;
+    constexpr size_t N3 = (size_t)N * N * N;
+    __shared__ __align__(16) cplx sm[N * TZ];
+    const int tg = threadIdx.x;
+    const int j = blockIdx.x / (N / TZ), kg = blockIdx.x % (N / TZ);
+    const size_t off = (size_t)j * N + kg * TZ;
+    cplx tw[A - 1];
+    load_twiddles<N, -1>(tw, twtab, tg / TZ);
+
+    cplx acc[UNITS][B];
+    int msq[UNITS][B];
+#pragma unroll
+    for (int m = 0; m < UNITS; ++m) {
+        const int u = tg + m * B * TZ;
+        const int z = u % TZ, k1 = u / TZ;
+        const int lj = mode_of<N>(j), lk = mode_of<N>(kg * TZ + z);
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) {
+            const int li = mode_of<N>(k1 + A * k2);
+            msq[m][k2] = li * li + lj * lj + lk * lk;
+            acc[m][k2] = make_double2(0.0, 0.0);
+        }
+    }
+    for (int r = 0; r < n_r_local; ++r) {
+        const cplx *src = Ph + (size_t)r * N3 + off;
+        x1_pass<N, -1>(sm, tw, tg, [&](int x, int z) { return src[(size_t)x * N * N + z]; });
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < UNITS; ++m) {
+            cplx v[B];
+            x2_unit<N, -1>(sm, tg, m, v);
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) {
+                const double c = __ldg(&coef[(size_t)r * M + msq[m][k2]]);
+                acc[m][k2].x += c * v[k2].x;
+                acc[m][k2].y += c * v[k2].y;
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < UNITS; ++m) {
+        const int u = tg + m * B * TZ;
+        const int z = u % TZ, k1 = u / TZ;
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2)
+            Qhat[off + (size_t)(k1 + A * k2) * N * N + z] = acc[m][k2];
+    }
+}
+
+// Q = Re(IFFT_x H0) - Re(IFFT_x H1) * f                 (cpp:304-330)
+template <int N>
+__global__ void __launch_bounds__(Geo<N>::B *TZ)
+k_pencil_final(const cplx *__restrict__ H, const cplx *__restrict__ twtab,
+               const double *f, double *Q)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS;
+    constexpr size_t N3 = (size_t)N * N * N;
+    __shared__ __align__(16) cplx sm[2][N * TZ];
+    const int tg = threadIdx.x;
+    const int y = blockIdx.x / (N / TZ), zg = blockIdx.x % (N / TZ);
+    const size_t off = (size_t)y * N + zg * TZ;
+    cplx tw[A - 1];
+    load_twiddles<N, +1>(tw, twtab, tg / TZ);
+    x1_pass<N, +1>(sm[0], tw, tg, [&](int x, int z) { return H[off + (size_t)x * N * N + z]; });
+    x1_pass<N, +1>(sm[1], tw, tg, [&](int x, int z) { return H[N3 + off + (size_t)x * N * N + z]; });
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < UNITS; ++m) {
+        cplx v0[B], v1[B];
+        const int k1 = x2_unit<N, +1>(sm[0], tg, m, v0);
+        x2_unit<N, +1>(sm[1], tg, m, v1);
+        const int z = (tg + m * B * TZ) % TZ;
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) {
+            const size_t idx = off + (size_t)(k1 + A * k2) * N * N + z;
+            const double fv = f[idx]; // read before the (possibly aliased) write below
+            Q[idx] = v0[k2].x - v1[k2].x * fv;
+        }
+    }
+}
+
+} // namespace bfsm

@@ -1,0 +1,123 @@
+/*
+ * bfsm_b200.h -- C ABI of the B200-native (sm_100a) fast Fourier-spectral Boltzmann
+ * collision operator Q(f,f).
+ *
+ * This is the drop-in boundary for ONE hot path of i3s93/Boltzmann-Fourier-Spectral-Method:
+ *   BoltzmannOperator<Backend>::computeCollision(double* Q, const double* f_in)
+ *     reference CPU:  Collisions/FFTWBoltzmannOperator.cpp:147-334   (parity oracle)
+ *     reference GPU:  Collisions/CUDABoltzmannOperator.cu:119-220 + BoltzmannCUDAKernels.cu:4-177
+ * A C++ class `BoltzmannOperator<B200_Backend>` (include/B200BoltzmannOperator.hpp) wraps these
+ * entry points behind the reference's AbstractCollisionOperator interface
+ * (Collisions/AbstractCollisionOperator.hpp:7-26); Python binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, a BFSM_ERR_* code
+ *     otherwise, and never calls exit(); bfsm_last_error() returns the message (thread local).
+ *   - grids are row-major (i*Nvy + j)*Nvz + k, z fastest, real fp64, N = Nvx*Nvy*Nvz values
+ *     (FFTWBoltzmannOperator.cpp:173).  This release supports cubic grids Nvx=Nvy=Nvz in
+ *     {16, 32, 64}; anything else is rejected with BFSM_ERR_UNSUPPORTED at plan creation.
+ *   - `*_dev` pointers are device pointers on the plan's device (the CUDA backend's convention,
+ *     CUDABoltzmannOperator.cu:119-134); `*_host` pointers are host pointers (the FFTW backend's).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer
+ *     calls are asynchronous on that stream; host-pointer calls return when the result is ready.
+ *   - Q may alias f_in (both reference backends tolerate it: FFTWBoltzmannOperator.cpp:168-180).
+ *   - a plan is not re-entrant (it owns its scratch memory), like the reference operators.
+ *   - there is NO CPU fallback: without a CUDA device plan creation fails.
+ */
+#ifndef BFSM_B200_H
+#define BFSM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BFSM_VERSION 100 /* 0.1.0 */
+
+enum {
+    BFSM_OK = 0,
+    BFSM_ERR_INVALID = 1,     /* bad argument (NULL pointer, non-positive size, bad shard) */
+    BFSM_ERR_UNSUPPORTED = 2, /* grid shape not supported by this build */
+    BFSM_ERR_CUDA = 3,        /* CUDA runtime error, message in bfsm_last_error() */
+    BFSM_ERR_NOMEM = 4
+};
+
+/* plan flags */
+#define BFSM_FLAG_NO_FOLD 1u /* transform every (r,sigma) pair even if the design is antipodal */
+
+typedef struct bfsm_plan bfsm_plan;
+
+int bfsm_version(void);
+const char *bfsm_last_error(void);
+
+/*
+ * Replaces BoltzmannOperator<Backend>::BoltzmannOperator(...) + initialize()
+ *   (FFTWBoltzmannOperator.hpp:30-36, .cpp:14-70; CUDABoltzmannOperator.hpp:48-54, .cu:28-115).
+ *
+ *   rho[n_r], w_r[n_r]      Gauss-Legendre nodes/weights on [0,R]  (GaussLegendre.hpp:10-24)
+ *   sx,sy,sz,w_s[n_s]       spherical quadrature nodes/weights     (SphericalDesign.cpp:38-48)
+ *   gamma, b_gamma, L       collision-kernel exponent/constant, domain half-width
+ *   device                  CUDA device ordinal
+ *   shard_index/shard_count this plan evaluates shard `shard_index` of the (r,sigma) pair list
+ *                           split into `shard_count` contiguous, equal (+-1) parts; 0/1 = all pairs.
+ *
+ * The work list is the N_r x N_sigma pair list; if every direction has a bit-exact antipode with
+ * equal weight (true for all nine reference ssXXX.NNN.txt files) only one of each antipodal pair
+ * is transformed with doubled weight -- pairs (r,s) and (r,-s) give bitwise identical g1*g2.
+ */
+int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r, const double *rho,
+                     const double *w_r, int n_s, const double *sx, const double *sy,
+                     const double *sz, const double *w_s, double gamma, double b_gamma, double L,
+                     int device, int shard_index, int shard_count, unsigned flags);
+
+/* Replaces ~BoltzmannOperator() (FFTWBoltzmannOperator.cpp:338-363). NULL is accepted. */
+int bfsm_plan_destroy(bfsm_plan *plan);
+
+/*
+ * Replaces computeCollision / operator() (FFTWBoltzmannOperator.cpp:147-334,
+ * CUDABoltzmannOperator.cu:119-220) for `n_cells` consecutive N-sized grids:
+ * Q_dev[c*N + idx] = Q(f,f)[idx] of cell c.  Requires shard_count == 1.
+ */
+int bfsm_collide(bfsm_plan *plan, double *Q_dev, const double *f_dev, int n_cells, void *stream);
+
+/* Same with host buffers: H2D copy of f, evaluation, D2H copy of Q, stream synchronised. */
+int bfsm_collide_host(bfsm_plan *plan, double *Q_host, const double *f_host, int n_cells,
+                      void *stream);
+
+/*
+ * Multi-GPU split of one evaluation (one cell).  Step 1 on every rank: this shard's partial
+ * gain spectrum  Qhat_dev[2*N] (complex, re/im interleaved) = sum over the shard's pairs of
+ * W_rs * beta1_r(|l|) * FFT3(Re(g1*g2))   (FFTWBoltzmannOperator.cpp:191-276 restricted to the
+ * shard).  Step 2: the caller sums Qhat over ranks (one ncclAllReduce of 2*N doubles).  Step 3:
+ * bfsm_finish() = loss term, inverse transform and combine (cpp:281-330).  bfsm_finish must be
+ * called with the same f_dev as the preceding bfsm_gain_hat on this plan (it reuses FFT3(f)).
+ *
+ * Only Re(g1*g2) is transformed: beta1 is real and even in l, so Im(g1*g2) only feeds
+ * Im(Q_gain), which the reference discards (cpp:326).  Hence Qhat is the Hermitian part of the
+ * reference's Q_gain_hat; Q is unchanged.
+ */
+int bfsm_gain_hat(bfsm_plan *plan, double *Qhat_dev, const double *f_dev, void *stream);
+int bfsm_finish(bfsm_plan *plan, double *Q_dev, const double *Qhat_dev, const double *f_dev,
+                void *stream);
+
+/* Introspection (used by bench.py for the roofline arithmetic and by tests). */
+typedef struct {
+    int n;                   /* points per axis */
+    int n_r, n_s;            /* quadrature sizes as given */
+    int folded;              /* 1 if antipodal folding is active */
+    int pairs_total;         /* size of the (possibly folded) work list, all shards */
+    int pairs_local;         /* pairs this plan transforms */
+    int chunk_pairs;         /* pairs per gain-kernel launch */
+    int launches_per_cell;   /* kernel launches issued per evaluated cell */
+    long long scratch_bytes; /* device memory owned by the plan */
+} bfsm_plan_info;
+
+int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);
+
+/* Tuning knob: pairs per launch of the gain kernels (0 = default heuristic). */
+int bfsm_plan_set_chunk(bfsm_plan *plan, int chunk_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BFSM_B200_H */
