@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py -- Q(f,f) evaluations per second of the B200 collision operator.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+A step is ONE evaluation Q(f,f) of one N^3 grid (BASELINE.json metric).  Default workload is
+BASELINE config 4 (the one the metric is quoted on): N=64^3, 32 Gauss-Legendre radii, 192-point
+spherical design.  With N>1 GPUs (launched by torch.distributed.run, one rank per GPU) the
+(r,sigma) pair list of that one evaluation is sharded over the ranks and the partial gain
+spectra are summed by one NCCL all-reduce per step: total work is fixed => "scaling": "strong".
+
+Timed region: K steps, each bracketed by CUDA events on the launching stream, the whole loop
+bracketed by barrier + torch.cuda.synchronize(); max over ranks.  Between steps 256 MiB are
+written to flush L2 (untimed; every evaluation also streams far more than L2 through the cache).
+
+Extra objects on the JSON line (see DESIGN.md "Measurement"):
+  roofline     dominant kernel class, algorithmic bytes per launch / mean launch duration,
+               measured live with CUDA events by bfsm_collide_profiled
+  cpu_baseline the reference CPU operator (oracle/_ref, unmodified reference sources + FFT
+               stand-in) timed on the host cores on a bounded sample of the same workload
+  e2e          same metric through the public operator with HOST buffers (H2D + D2H inside)
+
+`--impl reference` times only the reference CPU operator (rank 0) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (Nv, N_r, N_sigma)
+    "cfg4_64cubed_gl32_ss192": (64, 32, 192),
+    "cfg2_32cubed_gl16_ss32": (32, 16, 32),
+    "cfg1_16cubed_gl8_ss6": (16, 8, 6),
+    "cfg3_32cubed_gl32_ss48": (32, 32, 48),
+    "cfg5cell_32cubed_gl16_ss94": (32, 16, 94),
+}
+DEFAULT_WORKLOAD = "cfg4_64cubed_gl32_ss192"
+METRIC = "Q(f,f) evals/s"
+UNIT = "evals/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return json.load(fh), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling during the timed region."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- reference arm
+def reference_sample(Nv, n_r, n_s, steps, warmup, budget_s=25.0):
+    """Time the unmodified reference CPU operator on a bounded sample of the workload.
+
+    The reference allocates 96*N^3*P bytes (FFTWBoltzmannOperator.cpp:30-37): the full cfg-4 pair
+    list (6144 pairs, 154.6 GB) cannot exist in host memory, and one full evaluation would take
+    minutes.  Cost per pair is uniform (same transforms for every (r,sigma)), so the sample keeps
+    the grid and ALL spherical directions and reduces the number of radii to `n_r_sample`;
+    evals/s = 1 / (t_sample * n_r / n_r_sample).
+    """
+    import numpy as np
+    import bfsm_b200 as B
+    from oracle import oracle as O
+    inp = B.inputs
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    os.environ.setdefault("OMP_PLACES", "cores")       # slurm_run_maxwell_bkw_fftw.sb:30-31
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    f = inp.maxmix(Nv)
+    if O.reference_available():
+        kind = "reference"
+        # bytes of the reference's six batch arrays per radius
+        per_r = 96 * Nv ** 3 * n_s
+        n_r_sample = max(1, min(n_r, int(6e9 // per_r)))
+        # rough cost model to stay within the time budget: ~2e-7 s * N^3 log2-ish per pair per core
+        est_pair = {16: 3e-4, 32: 5e-3, 64: 5e-2}.get(Nv, 5e-2) / max(1, cores) * 1.5
+        n_r_sample = max(1, min(n_r_sample, int(budget_s / (steps + warmup) / (est_pair * n_s)) or 1))
+        op = O.ReferenceOperator(Nv, n_r_sample, n_s, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
+                                 inp.L_DOMAIN, a=0.0, b=inp.R_SUPPORT, threads=cores)
+        threads = op.max_threads()
+
+        def run():
+            return op(f, timed=True)[1]
+        label = "reference operator + shim FFT (FFTW unavailable in image)"
+    else:
+        kind = "port"
+        port = O.PortOracle()
+        port.set_threads(cores)
+        threads = port.max_threads()
+        n_r_sample = 1
+        gl = B.GaussLegendreQuadrature(n_r_sample, 0.0, inp.R_SUPPORT)
+        sd = B.SphericalDesign(n_s)
+        args = (gl.getNodes(), gl.getWeights(), sd.getx(), sd.gety(), sd.getz(), sd.getWeights(),
+                inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN)
+
+        def run():
+            t0 = time.perf_counter()
+            port.collide((Nv,) * 3, *args, f)
+            return time.perf_counter() - t0
+        label = "C port of the reference algorithm (oracle/bfsm_oracle.c)"
+    for _ in range(warmup):
+        run()
+    times = [run() for _ in range(steps)]
+    t_sample = sum(times) / len(times)
+    t_eval = t_sample * n_r / n_r_sample
+    sample = (f"{label}; {Nv}^3 grid, {n_r_sample} of {n_r} radii x all {n_s} directions "
+              f"({n_r_sample * n_s} of {n_r * n_s} pairs) per step, time scaled by {n_r}/{n_r_sample}; "
+              f"{steps} steps after {warmup} warm-up, OMP_NUM_THREADS={threads}")
+    return {"value": 1.0 / t_eval, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+            "seconds_per_eval": t_eval, "ms_per_step_sample": 1e3 * t_sample}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    Nv, n_r, n_s = WORKLOADS[args.workload]
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    cb = reference_sample(Nv, n_r, n_s, steps, warmup, budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+        "ms_per_step": 1e3 * cb["seconds_per_eval"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
+                   "input": "maxmix(seed=1234)"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import bfsm_b200 as B
+    inp = B.inputs
+    D = B.submodule("distributed")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    Nv, n_r, n_s = WORKLOADS[args.workload]
+    N3 = Nv ** 3
+    steps, warmup = max(1, args.steps), max(3, args.warmup)
+    gl = B.GaussLegendreQuadrature(n_r, 0.0, inp.R_SUPPORT)
+    sd = B.SphericalDesign(n_s)
+    op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
+                                 inp.L_DOMAIN, device=local_rank, shard_index=rank, shard_count=world)
+    op.initialize()
+    info = op.info()
+
+    f_host = torch.from_numpy(inp.maxmix(Nv)).reshape(-1).pin_memory()
+    q_host = torch.empty(N3, dtype=torch.float64).pin_memory()
+    f_dev = f_host.to(dev)
+    q_dev = torch.empty_like(f_dev)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
+
+    if world > 1:
+        sharded = D.PairShardedCollision(op, N3)
+
+        def step():
+            sharded(q_dev, f_dev)
+    else:
+        def step():
+            op(q_dev, f_dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(steps)]
+    barrier()
+    for a, b in ev:
+        flush.fill_(1.0)          # L2 flush, outside the event pair
+        a.record()
+        step()
+        b.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / steps
+    value = 1e3 / ms_per_step
+
+    # ---- end to end through the public operator with HOST buffers (H2D + D2H inside)
+    e2e_steps = steps
+    if world > 1:
+        def e2e_step():
+            f_dev.copy_(f_host, non_blocking=True)
+            sharded(q_dev, f_dev)
+            q_host.copy_(q_dev, non_blocking=True)
+            torch.cuda.synchronize()
+    else:
+        f_np, q_np = f_host.numpy(), q_host.numpy()
+
+        def e2e_step():
+            op(q_np, f_np)      # bfsm_collide_host: H2D, evaluate, D2H, stream sync
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_steps / float(t.item())
+
+    # ---- roofline of the dominant kernel class, measured live with CUDA events
+    roofline = None
+    prof = None
+    if world == 1:
+        op.profile(q_dev, f_dev)
+        prof = op.profile(q_dev, f_dev)
+        peaks, peak_src = measured_peaks()
+        pairs, chunk = info["pairs_local"], info["chunk_pairs"]
+        n_launch = (pairs + chunk - 1) // chunk
+        # algorithmic bytes per evaluation of each gain kernel (DESIGN.md "Kernels"):
+        #   k_plane_gain : read fhat once per launch, write both hybrid arrays of every pair
+        #   k_pencil_gain: read both hybrid arrays of every pair, read+write S_r once per launch
+        bytes_plane = 16 * N3 * (2 * pairs + n_launch)
+        bytes_pencil = 16 * N3 * (2 * pairs) + 16 * N3 * n_launch
+        cls = "plane_gain" if prof["plane_gain"][0] >= prof["pencil_gain"][0] else "pencil_gain"
+        ms, launches = prof[cls]
+        bytes_cls = bytes_plane if cls == "plane_gain" else bytes_pencil
+        achieved = bytes_cls / (ms * 1e-3) / 1e9
+        total_prof_ms = sum(v[0] for v in prof.values())
+        contract_bytes = 96 * N3 * info["pairs_total"] + 128 * N3
+        roofline = {
+            "bound": "hbm", "kernel": "k_" + cls, "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+            "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
+            else "fallback 6.65 TB/s (B200_PROFILING.md)",
+            "bytes_per_launch": bytes_cls / launches, "ms_per_launch": ms / launches,
+            "launches_per_eval": launches, "share_of_step": ms / total_prof_ms,
+            "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
+            "note": "hybrid scratch is sized to stay L2-resident, so DRAM traffic is far below the "
+                    "algorithmic bytes (see profiles/); frac is algorithmic bytes / time over the "
+                    "HBM copy peak",
+            "survey_contract": {
+                "bytes_per_eval": contract_bytes, "P_done": info["pairs_total"],
+                "folded": bool(info["folded"]),
+                "equivalent_gbs": contract_bytes * value / 1e9,
+                "equivalent_frac": contract_bytes * value / 1e9 / peaks["hbm_gbs"],
+            },
+        }
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = reference_sample(Nv, n_r, n_s, steps=2, warmup=1, budget_s=25.0)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
+                "input": "maxmix(seed=1234)", "pairs_transformed": info["pairs_total"],
+                "antipodal_folding": bool(info["folded"]), "chunk_pairs": info["chunk_pairs"],
+                "parallelism": f"pair-shard x{world}" if world > 1 else "single GPU",
+                "l2_flush": "256 MiB written between steps (untimed); each evaluation streams "
+                            ">> 126 MB through L2",
+            },
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N3,
+                    "d2h_bytes_per_step": 8 * N3},
+            "gpu_launches": info["launches_per_cell"] * steps,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -15,8 +15,10 @@ BFSM_FLAG_NO_FOLD = 1
 EXPORTS = (
     "bfsm_version", "bfsm_last_error", "bfsm_plan_create", "bfsm_plan_destroy", "bfsm_collide",
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
-    "bfsm_plan_set_chunk",
+    "bfsm_plan_set_chunk", "bfsm_collide_profiled",
 )
+
+KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final")
 
 
 class PlanInfo(ctypes.Structure):
@@ -69,6 +71,9 @@ def load():
     lib.bfsm_finish.argtypes = [vp, vp, vp, vp, vp]
     lib.bfsm_plan_get_info.restype = ctypes.c_int
     lib.bfsm_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfo)]
+    lib.bfsm_collide_profiled.restype = ctypes.c_int
+    lib.bfsm_collide_profiled.argtypes = [vp, vp, vp, vp, ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(ctypes.c_int)]
     lib.bfsm_plan_set_chunk.restype = ctypes.c_int
     lib.bfsm_plan_set_chunk.argtypes = [vp, ctypes.c_int]
     _lib = lib

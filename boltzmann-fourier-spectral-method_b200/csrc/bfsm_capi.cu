@@ -82,6 +82,13 @@ struct bfsm_plan {
     double *stage_f = nullptr, *stage_q = nullptr; // host-pointer entry point staging
     size_t stage_cells = 0;
     std::vector<void *> allocs;
+
+    // optional per-kernel-class timing (bfsm_collide_profiled)
+    bool profiling = false;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
 };
 
 namespace {
@@ -150,6 +157,38 @@ template <int N> int configure_kernels()
     return BFSM_OK;
 }
 
+// ---- optional CUDA-event bracket around one launch (same stream as the kernel) -----------
+cudaEvent_t prof_event(bfsm_plan *p)
+{
+    if (p->events_used == p->event_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        p->event_pool.push_back(e);
+    }
+    return p->event_pool[p->events_used++];
+}
+struct ProfSpan {
+    bfsm_plan *p;
+    cudaStream_t st;
+    int cls;
+    cudaEvent_t a = nullptr;
+    ProfSpan(bfsm_plan *p_, cudaStream_t st_, int cls_) : p(p_), st(st_), cls(cls_)
+    {
+        if (p->profiling) {
+            a = prof_event(p);
+            cudaEventRecord(a, st);
+        }
+    }
+    ~ProfSpan()
+    {
+        if (p->profiling) {
+            cudaEvent_t b = prof_event(p);
+            cudaEventRecord(b, st);
+            p->spans.push_back({cls, a, b});
+        }
+    }
+};
+
 // ---- one evaluation, split in the two halves the multi-GPU path needs -------------------
 
 // f -> fhat (scaled by 1/N^3) -> partial gain spectrum of this shard
@@ -161,9 +200,12 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     constexpr int TGP = Geo<N>::B * TZ;
 
     // forward transform of f (cpp:168-186)
-    k_plane<N, -1, PLANE_REAL><<<dim3(N, 1), N * Geo<N>::B, plane_smem<N>(), st>>>(
-        f, 1, 0, nullptr, nullptr, nullptr, p->tw, p->tmp);
-    k_pencil_fwd<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, 1.0 / (double)N3, p->fhat);
+    {
+        ProfSpan ps(p, st, BFSM_KCLASS_FORWARD);
+        k_plane<N, -1, PLANE_REAL><<<dim3(N, 1), N * Geo<N>::B, plane_smem<N>(), st>>>(
+            f, 1, 0, nullptr, nullptr, nullptr, p->tw, p->tmp);
+        k_pencil_fwd<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, 1.0 / (double)N3, p->fhat);
+    }
 
     // gain: S_r = sum_sigma w Re(g1 g2)
     CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)p->G * p->n_r_local * N3, st));
@@ -172,20 +214,29 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         const int items = 2 * nc;
         int gy = std::min(p->gy, (items + Lc::GROUPS - 1) / Lc::GROUPS);
         if (gy < 1) gy = 1;
-        k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
-            <<<dim3(N, gy), Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
-                p->fhat, p->phase, p->tw, p->hyb, c0, items);
+        {
+            ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
+            k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
+                <<<dim3(N, gy), Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
+                    p->fhat, p->phase, p->tw, p->hyb, c0, items);
+        }
         const int G = std::min(p->G, nc);
-        k_pencil_gain<N, Lc::PG><<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
-            p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+        {
+            ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
+            k_pencil_gain<N, Lc::PG><<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
+                p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+        }
     }
 
     // Qhat = sum_r coef_r(|l|^2) FFT3(S_r)   (cpp:249-273)
-    if (p->n_r_local > 0) {
-        k_plane<N, -1, PLANE_REAL><<<dim3(N, p->n_r_local), N * Geo<N>::B, plane_smem<N>(), st>>>(
-            p->S, p->G, (size_t)p->n_r_local * N3, nullptr, nullptr, nullptr, p->tw, p->tmp);
+    {
+        ProfSpan ps(p, st, BFSM_KCLASS_ACCUM);
+        if (p->n_r_local > 0) {
+            k_plane<N, -1, PLANE_REAL><<<dim3(N, p->n_r_local), N * Geo<N>::B, plane_smem<N>(), st>>>(
+                p->S, p->G, (size_t)p->n_r_local * N3, nullptr, nullptr, nullptr, p->tw, p->tmp);
+        }
+        k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
     }
-    k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
     CUDA_TRY(cudaGetLastError());
     return BFSM_OK;
 }
@@ -195,9 +246,12 @@ template <int N> int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const
 {
     constexpr int TILES = N * N / TZ;
     constexpr int TGP = Geo<N>::B * TZ;
-    k_plane<N, +1, PLANE_FINAL><<<dim3(N, 2), N * Geo<N>::B, plane_smem<N>(), st>>>(
-        nullptr, 0, 0, qhat, p->fhat, p->beta2, p->tw, p->tmp);
-    k_pencil_final<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, f, Q);
+    {
+        ProfSpan ps(p, st, BFSM_KCLASS_FINAL);
+        k_plane<N, +1, PLANE_FINAL><<<dim3(N, 2), N * Geo<N>::B, plane_smem<N>(), st>>>(
+            nullptr, 0, 0, qhat, p->fhat, p->beta2, p->tw, p->tmp);
+        k_pencil_final<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, f, Q);
+    }
     CUDA_TRY(cudaGetLastError());
     return BFSM_OK;
 }
@@ -433,6 +487,7 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     if (!p) return BFSM_OK;
     GuardDevice guard(p->device);
     for (void *q : p->allocs) cudaFree(q);
+    for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     if (p->stage_f) cudaFree(p->stage_f);
     if (p->stage_q) cudaFree(p->stage_q);
     delete p;
@@ -536,5 +591,32 @@ extern "C" int bfsm_collide_host(bfsm_plan *p, double *Q_host, const double *f_h
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(Q_host, p->stage_q, bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_collide_profiled(bfsm_plan *p, double *Q_dev, const double *f_dev, void *stream,
+                                     double *ms_by_class, int *launches_by_class)
+{
+    if (!p || !Q_dev || !f_dev || !ms_by_class || !launches_by_class)
+        return fail(BFSM_ERR_INVALID, "NULL argument");
+    GuardDevice guard(p->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    p->profiling = true;
+    p->spans.clear();
+    p->events_used = 0;
+    int rc = bfsm_collide(p, Q_dev, f_dev, 1, stream);
+    p->profiling = false;
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c = 0; c < BFSM_KCLASS_COUNT; ++c) {
+        ms_by_class[c] = 0.0;
+        launches_by_class[c] = 0;
+    }
+    for (const auto &sp : p->spans) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        ms_by_class[sp.cls] += (double)ms;
+        launches_by_class[sp.cls] += 1;
+    }
     return BFSM_OK;
 }

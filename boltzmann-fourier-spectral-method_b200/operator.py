@@ -158,6 +158,21 @@ class BoltzmannOperatorB200:
     def __call__(self, Q, f_in, **kw):
         return self.computeCollision(Q, f_in, **kw)
 
+    def profile(self, Q, f_in, stream=None):
+        """One evaluation with CUDA events around every launch group.
+
+        Returns {class name: (milliseconds, launch groups)} (see BFSM_KCLASS_* in bfsm_b200.h)."""
+        self._require()
+        self._check_dev(f_in, self.grid_size, "f_in")
+        self._check_dev(Q, self.grid_size, "Q")
+        n = len(_capi.KCLASS_NAMES)
+        ms = (ctypes.c_double * n)()
+        cnt = (ctypes.c_int * n)()
+        _capi.check(self._lib.bfsm_collide_profiled(
+            self._plan, ctypes.c_void_p(Q.data_ptr()), ctypes.c_void_p(f_in.data_ptr()),
+            self._stream(stream), ms, cnt))
+        return {name: (ms[i], cnt[i]) for i, name in enumerate(_capi.KCLASS_NAMES)}
+
     # ------------------------------------------------------------------ multi-GPU halves
     def gain_hat(self, Qhat, f_in, stream=None):
         """Qhat (2*N doubles, complex interleaved) <- this shard's partial gain spectrum."""

@@ -113,6 +113,23 @@ typedef struct {
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);
 
+/*
+ * Measurement aid (bench.py): one evaluation of one cell with a CUDA-event pair recorded on
+ * `stream` around every launch group; returns after synchronising the stream.
+ * ms_by_class[c] / launches_by_class[c] (arrays of BFSM_KCLASS_COUNT) receive the summed
+ * device time and the number of bracketed launch groups of each kernel class.
+ */
+enum {
+    BFSM_KCLASS_FORWARD = 0,     /* k_plane<REAL> + k_pencil_fwd : fhat = FFT3(f)          */
+    BFSM_KCLASS_PLANE_GAIN = 1,  /* k_plane_gain  : phase multiply + 2-D inverse FFT (y,z)  */
+    BFSM_KCLASS_PENCIL_GAIN = 2, /* k_pencil_gain : inverse FFT (x) + product + accumulate  */
+    BFSM_KCLASS_ACCUM = 3,       /* k_plane<REAL> + k_pencil_accum : Qhat = sum_r ...       */
+    BFSM_KCLASS_FINAL = 4,       /* k_plane<FINAL> + k_pencil_final : loss + combine        */
+    BFSM_KCLASS_COUNT = 5
+};
+int bfsm_collide_profiled(bfsm_plan *plan, double *Q_dev, const double *f_dev, void *stream,
+                          double *ms_by_class, int *launches_by_class);
+
 /* Tuning knob: pairs per launch of the gain kernels (0 = default heuristic). */
 int bfsm_plan_set_chunk(bfsm_plan *plan, int chunk_pairs);
 

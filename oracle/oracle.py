@@ -11,9 +11,11 @@
 Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this module.
 The product path (boltzmann-fourier-spectral-method_b200/) never does.
 """
+import contextlib
 import ctypes
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -189,6 +191,22 @@ class PortOracle:
 
 
 # ----------------------------------------------------------------------------- reference
+@contextlib.contextmanager
+def _quiet_stdout():
+    """The reference's initialize() prints "Failed to import wisdom ..." on std::cout
+    (FFTWBoltzmannOperator.cpp:60-62); keep it off our stdout (bench.py prints one JSON line)."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    try:
+        os.dup2(devnull, 1)
+        yield
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+        os.close(devnull)
+
+
 def reference_available():
     return os.path.exists(REF_LIB)
 
@@ -210,10 +228,11 @@ class ReferenceOperator:
             lib.bfsm_ref_set_threads(ctypes.c_int(int(threads)))
         self.shape = (Nv, Nv, Nv)
         self.n_gl, self.n_sph = n_gl, n_sph
-        self.h = lib.bfsm_ref_create(
-            ctypes.c_int(Nv), ctypes.c_int(Nv), ctypes.c_int(Nv), ctypes.c_int(n_gl),
-            ctypes.c_double(a), ctypes.c_double(b), ctypes.c_int(n_sph), ctypes.c_double(gamma),
-            ctypes.c_double(b_gamma), ctypes.c_double(L))
+        with _quiet_stdout():
+            self.h = lib.bfsm_ref_create(
+                ctypes.c_int(Nv), ctypes.c_int(Nv), ctypes.c_int(Nv), ctypes.c_int(n_gl),
+                ctypes.c_double(a), ctypes.c_double(b), ctypes.c_int(n_sph), ctypes.c_double(gamma),
+                ctypes.c_double(b_gamma), ctypes.c_double(L))
         if not self.h:
             raise RuntimeError("reference operator: " + lib.bfsm_ref_last_error().decode())
 
