@@ -59,7 +59,7 @@ struct bfsm_plan {
     int n_r_local = 0;
     int M = 0; // |l|^2 table length
     int chunk = 0;
-    int gy = 1;       // CTAs per plane in k_plane_gain
+    int gy = 1;       // persistent CTAs of k_plane_gain
     int G = 1;        // cross-CTA pair groups in k_pencil_gain (= number of S partials)
     int sm_count = 148;
     int shard_index = 0, shard_count = 1;
@@ -125,9 +125,9 @@ int env_int(const char *name, int dflt)
 
 // ---- per-N launch geometry ------------------------------------------------------------
 template <int N> struct Launch;
-template <> struct Launch<64> { static constexpr int TG = 256, GROUPS = 2, MINB = 1, PG = 4, G = 1, CHUNK = 8; };
-template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, G = 4, CHUNK = 64; };
-template <> struct Launch<16> { static constexpr int TG = 64, GROUPS = 2, MINB = 4, PG = 8, G = 8, CHUNK = 256; };
+template <> struct Launch<64> { static constexpr int TG = 256, GROUPS = 2, MINB = 1, PG = 4, PMINB = 2, G = 1, CHUNK = 96; };
+template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, PMINB = 2, G = 4, CHUNK = 256; };
+template <> struct Launch<16> { static constexpr int TG = 64, GROUPS = 2, MINB = 4, PG = 8, PMINB = 2, G = 8, CHUNK = 1024; };
 
 template <int N> size_t plane_gain_smem()
 {
@@ -147,7 +147,7 @@ template <int N> int configure_kernels()
     CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG>,
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_gain_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, -1, PLANE_REAL>,
@@ -212,18 +212,18 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk) {
         const int nc = std::min(p->chunk, p->pairs_local - c0);
         const int items = 2 * nc;
-        int gy = std::min(p->gy, (items + Lc::GROUPS - 1) / Lc::GROUPS);
-        if (gy < 1) gy = 1;
+        // persistent: one CTA per SM slot, never more CTAs than (plane, item-pair) units
+        int ctas = std::min(p->gy, std::max(1, (N * items) / Lc::GROUPS));
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
             k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
-                <<<dim3(N, gy), Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
+                <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
                     p->fhat, p->phase, p->tw, p->hyb, c0, items);
         }
         const int G = std::min(p->G, nc);
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
-            k_pencil_gain<N, Lc::PG><<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
+            k_pencil_gain<N, Lc::PG, Lc::PMINB><<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
                 p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
         }
     }
@@ -450,9 +450,8 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     p->chunk = std::min(p->chunk, std::max(1, p->pairs_local));
     p->G = (N == 64) ? Launch<64>::G : (N == 32) ? Launch<32>::G : Launch<16>::G;
     {
-        const int occ = (N == 64) ? 1 : (N == 32) ? 3 : 8;
-        int gy = (p->sm_count * occ) / N;
-        p->gy = std::max(1, env_int("BFSM_GAIN_GY", std::max(1, gy)));
+        const int occ = (N == 64) ? 1 : (N == 32) ? 2 : 4;
+        p->gy = std::max(1, env_int("BFSM_GAIN_CTAS", p->sm_count * occ));
     }
 
     int rc = BFSM_OK;

@@ -27,8 +27,10 @@
 namespace bfsm {
 
 // ---------------------------------------------------------------------------------------
-// k_plane_gain: grid (N planes, Gy), block GROUPS*TG.  Work item `it` of plane i is
-// (pair pl = it/2, array it&1); group g of CTA y owns items (y*GROUPS+g) + m*Gy*GROUPS.
+// k_plane_gain: persistent grid (about one CTA per SM slot), block GROUPS*TG.  The flat work
+// list (plane i, item it) with it = 2*pair + array is split evenly over the CTAs; a CTA walks
+// its range plane by plane (reloading the fhat plane when it changes) and its GROUPS groups
+// take the items of a plane alternately.
 // Shared memory: fhat plane (N*N) | GROUPS padded planes (N*ROW) | GROUPS x 2 phase slots (3N).
 // ---------------------------------------------------------------------------------------
 template <int N, int TG, int GROUPS, int MINB>
@@ -37,70 +39,80 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
              const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
-    constexpr int N3 = N * N * N;
     static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *fpl = reinterpret_cast<cplx *>(smem_raw);
     cplx *bufs = fpl + N * N;
     cplx *phs = bufs + GROUPS * N * ROW;
 
-    const int i = blockIdx.x;
     const int g = threadIdx.x / TG, tg = threadIdx.x % TG;
     cplx *buf = bufs + g * N * ROW;
     cplx *myph = phs + g * 2 * 3 * N;
 
-    for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = fhat[(size_t)i * N * N + t];
-
     cplx tw[A - 1];
     load_twiddles<N, +1>(tw, twtab, tg % B);
 
-    const int stride = gridDim.y * GROUPS;
-    const int first = blockIdx.y * GROUPS + g;
-    if (first < n_items && tg < 3 * N)
-        myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> 1)) * 3 * N + tg]);
-    __syncthreads();
+    // flat work list: index = plane * n_items + item; this CTA owns [w_lo, w_hi)
+    const long long total = (long long)N * n_items;
+    const int w_lo = (int)((total * blockIdx.x) / gridDim.x);
+    const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
 
-    int slot = 0;
-    for (int it = first; it < n_items; it += stride, slot ^= 1) {
-        const int arr = it & 1;
-        const cplx *P = myph + slot * 3 * N;
-        const bool have_next = (it + stride < n_items) && (tg < 3 * N);
-        cplx nxt = make_double2(0.0, 0.0);
-        if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + stride) >> 1)) * 3 * N + tg]);
-        const cplx exi = P[i];
+    int w = w_lo;
+    while (w < w_hi) {
+        const int i = w / n_items;                       // plane of this segment
+        const int it_lo = w - i * n_items;
+        int it_hi = n_items;
+        if ((long long)(i + 1) * n_items > w_hi) it_hi = w_hi - i * n_items;
 
-        // z pass 1 with the phase-weighted load fused in (cpp:198-225):
-        // A1 = e^{i theta} fhat, A2 = e^{-i theta} fhat, theta separable in (i,j,k).
+        __syncthreads(); // every group is done with the previous plane
+        for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = fhat[(size_t)i * N * N + t];
+        const int first = it_lo + g;
+        if (first < it_hi && tg < 3 * N)
+            myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> 1)) * 3 * N + tg]);
+        __syncthreads();
+
+        int slot = 0;
+        for (int it = first; it < it_hi; it += GROUPS, slot ^= 1) {
+            const int arr = it & 1;
+            const cplx *P = myph + slot * 3 * N;
+            const bool have_next = (it + GROUPS < it_hi) && (tg < 3 * N);
+            cplx nxt = make_double2(0.0, 0.0);
+            if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + GROUPS) >> 1)) * 3 * N + tg]);
+            const cplx exi = P[i];
+
+            // z pass 1 with the phase-weighted load fused in (cpp:198-225):
+            // A1 = e^{i theta} fhat, A2 = e^{-i theta} fhat, theta separable in (i,j,k).
 #pragma unroll
-        for (int u0 = 0; u0 < N * B; u0 += TG) {
-            const int u = u0 + tg;
-            const int j = u / B, b = u % B;
-            const cplx exy = cmul(exi, P[N + j]);
-            cplx v[A];
+            for (int u0 = 0; u0 < N * B; u0 += TG) {
+                const int u = u0 + tg;
+                const int j = u / B, b = u % B;
+                const cplx exy = cmul(exi, P[N + j]);
+                cplx v[A];
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-                const int k = B * a + b;
-                const cplx e = cmul(exy, P[2 * N + k]);
-                const cplx f = fpl[j * N + k];
-                v[a] = arr ? cmulc(f, e) : cmul(f, e);
+                for (int a = 0; a < A; ++a) {
+                    const int k = B * a + b;
+                    const cplx e = cmul(exy, P[2 * N + k]);
+                    const cplx f = fpl[j * N + k];
+                    v[a] = arr ? cmulc(f, e) : cmul(f, e);
+                }
+                Dft<A, +1>::run(v);
+                cplx *row = buf + j * ROW;
+                row[padk(b)] = v[0];
+#pragma unroll
+                for (int k1 = 1; k1 < A; ++k1) row[padk(B * k1 + b)] = cmul(v[k1], tw[k1 - 1]);
             }
-            Dft<A, +1>::run(v);
-            cplx *row = buf + j * ROW;
-            row[padk(b)] = v[0];
-#pragma unroll
-            for (int k1 = 1; k1 < A; ++k1) row[padk(B * k1 + b)] = cmul(v[k1], tw[k1 - 1]);
+            group_sync(1 + g, TG);
+            z2_pass<N, +1, TG>(buf, tg);
+            group_sync(1 + g, TG);
+            if (have_next) myph[(slot ^ 1) * 3 * N + tg] = nxt;
+            y1_pass<N, +1, TG>(buf, tw, tg);
+            group_sync(1 + g, TG);
+            cplx *dst = hyb + ((size_t)it * N + i) * N * N;
+            y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { dst[y * N + z] = val; });
+            group_sync(1 + g, TG);
         }
-        group_sync(1 + g, TG);
-        z2_pass<N, +1, TG>(buf, tg);
-        group_sync(1 + g, TG);
-        if (have_next) myph[(slot ^ 1) * 3 * N + tg] = nxt;
-        y1_pass<N, +1, TG>(buf, tw, tg);
-        group_sync(1 + g, TG);
-        cplx *dst = hyb + ((size_t)it * N + i) * N * N;
-        y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { dst[y * N + z] = val; });
-        group_sync(1 + g, TG);
+        w = i * n_items + it_hi;
     }
-    (void)N3;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -110,8 +122,8 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 // the forward FFT).  At every change of radius r the PG partial sums are reduced through
 // shared memory in fixed order and added to S[gy][r] -- no atomics, deterministic.
 // ---------------------------------------------------------------------------------------
-template <int N, int PG>
-__global__ void __launch_bounds__(PG *Geo<N>::B *TZ)
+template <int N, int PG, int MINB>
+__global__ void __launch_bounds__(PG *Geo<N>::B *TZ, MINB)
 k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
               const int *__restrict__ pair_r, const double *__restrict__ pair_w,
               const int *__restrict__ r_end, double *__restrict__ S, int pair0, int n_pairs_chunk,

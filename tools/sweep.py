@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Quick device-side timing sweep over BFSM_CHUNK_PAIRS / BFSM_GAIN_GY (tuning aid, not a benchmark)."""
+"""Quick device-side timing sweep over BFSM_CHUNK_PAIRS / BFSM_GAIN_CTAS (tuning aid, not a benchmark)."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -8,8 +8,8 @@ inp = B.inputs
 
 def run(Nv, n_r, n_s, chunk, gy=None, reps=2):
     os.environ["BFSM_CHUNK_PAIRS"] = str(chunk)
-    if gy: os.environ["BFSM_GAIN_GY"] = str(gy)
-    else: os.environ.pop("BFSM_GAIN_GY", None)
+    if gy: os.environ["BFSM_GAIN_CTAS"] = str(gy)
+    else: os.environ.pop("BFSM_GAIN_CTAS", None)
     gl = B.GaussLegendreQuadrature(n_r, 0.0, inp.R_SUPPORT); sd = B.SphericalDesign(n_s)
     op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN)
     op.initialize()
@@ -30,10 +30,10 @@ def run(Nv, n_r, n_s, chunk, gy=None, reps=2):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "64"
     if which == "64":
-        for chunk in (2, 4, 6, 8, 12, 16, 24):
+        for chunk in (8, 16, 24, 32, 48, 96):
             run(64, 8, 192, chunk)
-        for gy in (1, 2, 3, 4):
-            run(64, 8, 192, 8, gy)
+        for ctas in (128, 148, 296):
+            run(64, 8, 192, 24, ctas)
     elif which == "32":
         for chunk in (16, 32, 64, 128, 256):
             run(32, 16, 32, chunk)
