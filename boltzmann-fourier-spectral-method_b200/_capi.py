@@ -15,7 +15,8 @@ BFSM_FLAG_NO_FOLD = 1
 EXPORTS = (
     "bfsm_version", "bfsm_last_error", "bfsm_plan_create", "bfsm_plan_destroy", "bfsm_collide",
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
-    "bfsm_plan_set_chunk", "bfsm_collide_profiled",
+    "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
+    "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host",
 )
 
 KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final")

@@ -619,3 +619,46 @@ extern "C" int bfsm_collide_profiled(bfsm_plan *p, double *Q_dev, const double *
     }
     return BFSM_OK;
 }
+
+extern "C" int bfsm_sync(bfsm_plan *p, void *stream)
+{
+    if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
+    GuardDevice guard(p->device);
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_device_malloc(int device, void **ptr, unsigned long long bytes)
+{
+    if (!ptr) return fail(BFSM_ERR_INVALID, "ptr is NULL");
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaMalloc(ptr, (size_t)bytes));
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_device_free(int device, void *ptr)
+{
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaFree(ptr));
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_copy_to_device(int device, void *dst_dev, const void *src_host,
+                                   unsigned long long bytes)
+{
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaMemcpy(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice));
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_copy_to_host(int device, void *dst_host, const void *src_dev,
+                                 unsigned long long bytes)
+{
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return BFSM_OK;
+}

@@ -99,6 +99,16 @@ int bfsm_gain_hat(bfsm_plan *plan, double *Qhat_dev, const double *f_dev, void *
 int bfsm_finish(bfsm_plan *plan, double *Q_dev, const double *Qhat_dev, const double *f_dev,
                 void *stream);
 
+/* cudaStreamSynchronize(stream) on the plan's device. */
+int bfsm_sync(bfsm_plan *plan, void *stream);
+
+/* Device-memory helpers so that C/C++ hosts can link this library alone (no CUDA headers):
+ * thin wrappers over cudaMalloc / cudaFree / cudaMemcpy on device ordinal `device`. */
+int bfsm_device_malloc(int device, void **ptr, unsigned long long bytes);
+int bfsm_device_free(int device, void *ptr);
+int bfsm_copy_to_device(int device, void *dst_dev, const void *src_host, unsigned long long bytes);
+int bfsm_copy_to_host(int device, void *dst_host, const void *src_dev, unsigned long long bytes);
+
 /* Introspection (used by bench.py for the roofline arithmetic and by tests). */
 typedef struct {
     int n;                   /* points per axis */

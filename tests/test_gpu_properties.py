@@ -1,0 +1,228 @@
+"""GPU tests beyond the plain parity sweep: golden fixtures of the reference, the boundary's
+pointer/aliasing/batch semantics, the multi-GPU split, determinism, and size-independent
+properties at BASELINE.json's full sizes (where the CPU oracle is too slow to run)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import bfsm_b200 as B
+from helpers import REL_LINF_TOL, inp, make_input, make_operator, oracle_args, quadrature, rel_linf
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VECTORS = np.load(os.path.join(ROOT, "tests", "golden", "reference_q_vectors.npz"))
+
+
+def _eval(op, f):
+    f_dev = torch.from_numpy(np.ascontiguousarray(f)).cuda().reshape(-1)
+    Q_dev = torch.empty_like(f_dev)
+    op(Q_dev, f_dev)
+    torch.cuda.synchronize()
+    return Q_dev.cpu().numpy()
+
+
+def _golden_cases():
+    for key in VECTORS.files:
+        if key.endswith("_Q"):
+            nv, r, s, kind = key[:-2].split("_")
+            yield int(nv[2:]), int(r[1:]), int(s[1:]), kind
+
+
+@pytest.mark.parametrize("Nv,n_r,n_s,kind", list(_golden_cases()))
+def test_matches_reference_golden_vectors(Nv, n_r, n_s, kind):
+    """Q arrays written by the UNMODIFIED reference operator (tests/golden/make_golden.py)."""
+    op, _, _ = make_operator(Nv, n_r, n_s)
+    err = rel_linf(_eval(op, make_input(kind, Nv)), VECTORS[f"Nv{Nv}_r{n_r}_s{n_s}_{kind}_Q"])
+    assert err <= REL_LINF_TOL, err
+
+
+def test_bkw_error_norms_match_published_known_answer():
+    """32^3, N_gl=32, 12-point design: Results/maxwell_bkw_fftw_atomics.txt:19-21; north_star asks
+    for the BKW error to match the reference's within 1 %."""
+    Nv = 32
+    op, _, _ = make_operator(Nv, 32, 12)
+    f, Q_exact = inp.bkw(Nv)
+    l1, l2, linf = inp.error_norms(_eval(op, f), Q_exact, Nv)
+    assert abs(l1 - 1.54029638e-03) <= 1e-7 * 1.54029638e-03
+    assert abs(l2 - 1.01189917e-04) <= 1e-7 * 1.01189917e-04
+    assert abs(linf - 4.25120273e-05) <= 1e-7 * 4.25120273e-05
+
+
+def test_folding_is_exact(port_oracle):
+    """Antipodal folding (N_sigma/2 transforms, weight x2) against transforming every pair."""
+    Nv, n_r, n_s = 16, 4, 12
+    f = make_input("noise", Nv)
+    op_f, gl, sd = make_operator(Nv, n_r, n_s)
+    op_u, _, _ = make_operator(Nv, n_r, n_s, fold=False)
+    assert op_f.info()["folded"] == 1 and op_f.info()["pairs_total"] == n_r * n_s // 2
+    assert op_u.info()["folded"] == 0 and op_u.info()["pairs_total"] == n_r * n_s
+    Q_ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    assert rel_linf(_eval(op_f, f), Q_ref) <= REL_LINF_TOL
+    assert rel_linf(_eval(op_u, f), Q_ref) <= REL_LINF_TOL
+
+
+def test_non_antipodal_quadrature_falls_back_to_all_pairs(port_oracle):
+    Nv, n_r = 16, 3
+    gl = B.GaussLegendreQuadrature(n_r, 0.0, inp.R_SUPPORT)
+    rng = np.random.default_rng(3)
+    pts = rng.standard_normal((5, 3))
+    pts /= np.linalg.norm(pts, axis=1)[:, None]
+    sq = B.SphericalQuadrature(pts[:, 0], pts[:, 1], pts[:, 2], rng.uniform(0.5, 1.5, 5))
+    op = B.BoltzmannOperatorB200(gl, sq, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN)
+    op.initialize()
+    assert op.info()["folded"] == 0 and op.info()["pairs_total"] == 15
+    f = make_input("maxmix", Nv)
+    Q_ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sq), f)
+    assert rel_linf(_eval(op, f), Q_ref) <= REL_LINF_TOL
+
+
+def test_variable_hard_sphere_exponent(port_oracle):
+    """gamma != 0 only changes host-side weights (FFTWBoltzmannOperator.cpp:252,292)."""
+    Nv, n_r, n_s = 16, 6, 12
+    gl, sd = quadrature(n_r, n_s)
+    op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 1.0, 0.3, inp.L_DOMAIN)
+    op.initialize()
+    f = make_input("maxmix", Nv)
+    Q_ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd, gamma=1.0, b_gamma=0.3), f)
+    assert rel_linf(_eval(op, f), Q_ref) <= REL_LINF_TOL
+
+
+def test_host_pointer_entry_point_and_aliasing(port_oracle):
+    Nv, n_r, n_s = 16, 8, 6
+    op, gl, sd = make_operator(Nv, n_r, n_s)
+    f = make_input("maxmix", Nv)
+    Q_ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    Q_host = np.empty_like(f)
+    op(Q_host, f)                                   # host pointers: H2D + evaluate + D2H inside
+    assert rel_linf(Q_host, Q_ref) <= REL_LINF_TOL
+    buf = torch.from_numpy(f.copy()).cuda().reshape(-1)
+    op(buf, buf)                                    # Q aliases f_in (both reference backends allow it)
+    torch.cuda.synchronize()
+    assert rel_linf(buf.cpu().numpy(), Q_ref) <= REL_LINF_TOL
+
+
+def test_batch_of_cells_matches_cell_by_cell(port_oracle):
+    Nv, n_r, n_s, cells = 16, 4, 12, 5
+    op, gl, sd = make_operator(Nv, n_r, n_s)
+    fs = np.stack([make_input("maxmix", Nv, seed=c) for c in range(cells)])
+    f_dev = torch.from_numpy(fs).cuda().reshape(-1)
+    Q_dev = torch.empty_like(f_dev)
+    op(Q_dev, f_dev, n_cells=cells)
+    torch.cuda.synchronize()
+    Q = Q_dev.cpu().numpy().reshape(cells, Nv, Nv, Nv)
+    for c in (0, cells - 1):
+        Q_ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), fs[c])
+        assert rel_linf(Q[c], Q_ref) <= REL_LINF_TOL
+    one = _eval(op, fs[2])
+    assert np.array_equal(one.ravel(), Q[2].ravel())      # same arithmetic in batch and single mode
+    op(Q_dev, f_dev, n_cells=0)                           # empty batch is a no-op
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pair_shards_sum_to_the_full_result(port_oracle, world):
+    """Emulates `world` ranks on one GPU: partial gain spectra summed on the host, finished by
+    every 'rank'; compared with the oracle's Hermitian-projected spectrum and with Q."""
+    Nv, n_r, n_s = 16, 5, 12
+    gl, sd = quadrature(n_r, n_s)
+    f = make_input("noise", Nv)
+    f_dev = torch.from_numpy(f).cuda().reshape(-1)
+    ops = []
+    total = torch.zeros(2 * Nv ** 3, dtype=torch.float64, device="cuda")
+    for r in range(world):
+        op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
+                                     shard_index=r, shard_count=world)
+        op.initialize()
+        part = torch.empty_like(total)
+        op.gain_hat(part, f_dev)
+        total += part
+        ops.append(op)
+    assert sum(o.info()["pairs_local"] for o in ops) == ops[0].info()["pairs_total"]
+    args = oracle_args(gl, sd)
+    ref_hat = O.hermitian_part(port_oracle.gain_hat((Nv,) * 3, *args, f, 0, n_r * n_s))
+    got_hat = total.cpu().numpy().view(np.complex128).reshape(Nv, Nv, Nv)
+    assert np.abs(got_hat - ref_hat).max() / np.abs(ref_hat).max() <= REL_LINF_TOL
+    Q_ref = port_oracle.collide((Nv,) * 3, *args, f)
+    for op in ops:
+        Q = torch.empty(Nv ** 3, dtype=torch.float64, device="cuda")
+        op.finish(Q, total, f_dev)
+        torch.cuda.synchronize()
+        assert rel_linf(Q.cpu().numpy(), Q_ref) <= REL_LINF_TOL
+    with pytest.raises(Exception):
+        ops[0](torch.empty_like(f_dev), f_dev)     # bfsm_collide refuses a sharded plan
+
+
+def test_deterministic_and_chunk_independent():
+    """No atomics anywhere: repeated evaluations are bitwise identical; the pair-chunk size only
+    changes the order of the final per-radius additions."""
+    Nv, n_r, n_s = 32, 4, 32
+    op, _, _ = make_operator(Nv, n_r, n_s)
+    f = make_input("noise", Nv)
+    a, b = _eval(op, f), _eval(op, f)
+    assert np.array_equal(a, b)
+    op.set_chunk(3)
+    c = _eval(op, f)
+    assert rel_linf(c, a) <= 1e-13
+
+
+# ---------------------------------------------------------------- full BASELINE sizes
+FULL = [(64, 32, 192), (32, 16, 94)]
+
+
+@pytest.mark.parametrize("Nv,n_r,n_s", FULL)
+def test_full_size_properties(Nv, n_r, n_s):
+    """cfg 4 (64^3, 32 x 192) and one cfg-5 cell (32^3, 16 x 94): the oracle needs minutes there,
+    so check exact algebraic properties instead:
+      * Q(2f) == 4 Q(f) bitwise (Q is quadratic; scaling by 2 is exact in binary fp),
+      * shard-sum: gain spectra of 4 pair shards add up to the unsharded spectrum,
+      * the BKW error stays at the reference's level (64^3: ~1e-10, published :195-197)."""
+    op, gl, sd = make_operator(Nv, n_r, n_s)
+    f = make_input("maxmix", Nv)
+    Q1 = _eval(op, f)
+    Q2 = _eval(op, 2.0 * f)
+    assert np.array_equal(Q2, 4.0 * Q1)
+    f_dev = torch.from_numpy(f).cuda().reshape(-1)
+    full = torch.empty(2 * Nv ** 3, dtype=torch.float64, device="cuda")
+    op.gain_hat(full, f_dev)
+    acc = torch.zeros_like(full)
+    for r in range(4):
+        sh = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
+                                     shard_index=r, shard_count=4)
+        sh.initialize()
+        part = torch.empty_like(full)
+        sh.gain_hat(part, f_dev)
+        acc += part
+        sh.close()
+    torch.cuda.synchronize()
+    assert float((acc - full).abs().max() / full.abs().max()) <= 1e-13
+    fb, Qb = inp.bkw(Nv)
+    l1, l2, linf = inp.error_norms(_eval(op, fb), Qb, Nv)
+    if Nv == 64:
+        assert l1 < 2e-10 and l2 < 2e-11 and linf < 1e-11
+    else:
+        assert abs(l1 - 1.10408785e-03) < 1e-2 * 1.10408785e-03   # survey's provisional 32/16/94 value
+
+
+def test_cpp_driver_reproduces_known_answer():
+    """The C++ BoltzmannOperator<B200_Backend> class driven like maxwell_bkw_cuda.cu."""
+    exe = os.path.join(ROOT, "boltzmann-fourier-spectral-method_b200", "drivers", "build",
+                       "maxwell_bkw_b200")
+    designs = os.path.join(ROOT, "oracle", "_ref", "designs")
+    if not (os.path.exists(exe) and os.path.isdir(designs)):
+        pytest.skip("driver or design files not built")
+    out = subprocess.run([exe, "--Nv", "32", "--Ns", "12", "-t", "2", "--design-dir", designs],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    vals = {}
+    for line in out.stdout.splitlines():
+        for key in ("L1 error", "L2 error", "Linf error"):
+            if line.startswith(key):
+                vals[key] = float(line.split(":")[1])
+    assert abs(vals["L1 error"] - 1.54029638e-03) <= 1e-7 * 1.54029638e-03
+    assert abs(vals["L2 error"] - 1.01189917e-04) <= 1e-7 * 1.01189917e-04
+    assert abs(vals["Linf error"] - 4.25120273e-05) <= 1e-7 * 4.25120273e-05
+    assert "Run statistics for B200" in out.stdout

@@ -1,0 +1,145 @@
+"""CPU tests of the host-side logic and of the C-ABI boundary (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import bfsm_b200 as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+capi = B.submodule("_capi")
+D = B.submodule("distributed")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
+        header = fh.read()
+    declared = set(re.findall(r"\b(bfsm_[a-z_0-9]+)\s*\(", header))
+    declared -= {"bfsm_plan", "bfsm_plan_info"}
+    assert declared, "no declarations parsed"
+    lib = capi.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in bfsm_b200.h but not exported"
+    assert set(capi.EXPORTS) == declared
+    assert lib.bfsm_version() == 100
+
+
+def _create(lib, nv=(16, 16, 16), n_r=2, n_s=6, shard=(0, 1), L=1.0, null_rho=False):
+    dp = ctypes.POINTER(ctypes.c_double)
+    rho = np.array([1.0, 2.0][:n_r] + [1.0] * max(0, n_r - 2))
+    w = np.ones(max(n_r, 1))
+    sd = B.SphericalDesign(6)
+    plan = ctypes.c_void_p()
+    rc = lib.bfsm_plan_create(
+        ctypes.byref(plan), nv[0], nv[1], nv[2], n_r,
+        None if null_rho else rho.ctypes.data_as(dp), w.ctypes.data_as(dp), n_s,
+        sd.getx().ctypes.data_as(dp), sd.gety().ctypes.data_as(dp), sd.getz().ctypes.data_as(dp),
+        sd.getWeights().ctypes.data_as(dp), 0.0, 1.0, L, 0, shard[0], shard[1], 0)
+    return rc, plan
+
+
+def test_plan_create_argument_errors_are_reported_not_fatal():
+    lib = capi.load()
+    rc, _ = _create(lib, null_rho=True)
+    assert rc == capi.BFSM_ERR_INVALID and b"NULL" in lib.bfsm_last_error()
+    rc, _ = _create(lib, n_r=0)
+    assert rc == capi.BFSM_ERR_INVALID
+    rc, _ = _create(lib, L=-1.0)
+    assert rc == capi.BFSM_ERR_INVALID
+    rc, _ = _create(lib, shard=(3, 2))
+    assert rc == capi.BFSM_ERR_INVALID
+    rc, _ = _create(lib, nv=(16, 16, 32))
+    assert rc == capi.BFSM_ERR_UNSUPPORTED and b"not supported" in lib.bfsm_last_error()
+    rc, _ = _create(lib, nv=(24, 24, 24))
+    assert rc == capi.BFSM_ERR_UNSUPPORTED
+    assert lib.bfsm_plan_destroy(None) == capi.BFSM_OK
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    lib = capi.load()
+    rc, _ = _create(lib)
+    assert rc == capi.BFSM_ERR_CUDA
+    assert b"no CPU fallback" in lib.bfsm_last_error()
+    gl = B.GaussLegendreQuadrature(4, 0.0, 10.0)
+    op = B.BoltzmannOperatorB200(gl, B.SphericalDesign(6), 16, 16, 16, 0.0, 1.0, 1.0)
+    with pytest.raises(RuntimeError):
+        op.initialize()
+    with pytest.raises(RuntimeError):
+        op.computeCollision(np.zeros(4096), np.zeros(4096))
+
+
+def test_gauss_legendre_against_numpy_and_exactness():
+    for n in (1, 2, 5, 8, 16, 32, 64):
+        gl = B.GaussLegendreQuadrature(n, 0.0, 10.0)
+        x, w = np.polynomial.legendre.leggauss(n)
+        assert np.abs(gl.getNodes() - (5 + 5 * x)).max() < 5e-14
+        assert np.abs(gl.getWeights() - 5 * w).max() < 5e-14
+        assert np.all(np.diff(gl.getNodes()) > 0)            # ascending, GaussLegendre.hpp:19-21
+        assert gl.getNumberOfPoints() == n
+        # exact for polynomials up to degree 2n-1
+        k = 2 * n - 1
+        assert abs((gl.getWeights() * gl.getNodes() ** k).sum() - 10.0 ** (k + 1) / (k + 1)) \
+            <= 1e-13 * 10.0 ** (k + 1)
+    with pytest.raises(ValueError):
+        B.GaussLegendreQuadrature(0, 0.0, 1.0)
+
+
+def test_spherical_designs():
+    for n, degree in {6: 3, 12: 5, 32: 7, 48: 9, 70: 11, 94: 13, 120: 15, 156: 17, 192: 19}.items():
+        sd = B.SphericalDesign(n)
+        assert sd.getNumberOfPoints() == n
+        r = np.sqrt(sd.getx() ** 2 + sd.gety() ** 2 + sd.getz() ** 2)
+        assert np.abs(r - 1).max() < 1e-14
+        assert np.all(sd.getWeights() == (4 * B.pi) / n)      # SphericalDesign.cpp:48
+        assert sd.is_antipodal()
+        # a t-design integrates odd monomials to zero and x^2 to 4 pi / 3
+        assert abs((sd.getWeights() * sd.getx() ** 3).sum()) < 1e-13
+        assert abs((sd.getWeights() * sd.getx() ** 2).sum() - 4 * B.pi / 3) < 1e-13
+    with pytest.raises(ValueError):
+        B.SphericalDesign(0)                                   # SphericalDesign.cpp:7-9
+    with pytest.raises(ValueError):
+        B.SphericalDesign(7)                                   # SphericalDesign.cpp:22-23
+
+
+def test_design_directory_loader(tmp_path):
+    sd = B.SphericalDesign(6)
+    with open(tmp_path / "ss003.006.txt", "w") as fh:
+        for x, y, z in zip(sd.getx(), sd.gety(), sd.getz()):
+            fh.write(f"  {x: .16e}  {y: .16e}  {z: .16e}\n")
+    sd2 = B.SphericalDesign(6, design_dir=str(tmp_path))
+    assert np.array_equal(sd2.getx(), sd.getx()) and np.array_equal(sd2.getz(), sd.getz())
+    with pytest.raises(RuntimeError):
+        B.SphericalDesign(12, design_dir=str(tmp_path))        # SphericalDesign.cpp:29-31
+
+
+def test_non_antipodal_quadrature_detected():
+    q = B.SphericalQuadrature([1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0], [1.0, 1.0, 1.0])
+    assert not q.is_antipodal()
+    q2 = B.SphericalQuadrature([1.0, -1.0], [0.0, -0.0], [0.0, -0.0], [1.0, 2.0])
+    assert not q2.is_antipodal()                               # unequal weights
+
+
+def test_shard_ranges_partition_the_work_list():
+    for total in (0, 1, 7, 48, 3072, 6144):
+        for count in (1, 2, 3, 4, 8):
+            edges = [D.shard_range(total, i, count) for i in range(count)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(edges, edges[1:]))
+            sizes = [hi - lo for lo, hi in edges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        D.shard_range(10, 2, 2)
+
+
+def test_bkw_input_is_a_normalised_density():
+    Nv = 32
+    f, Q = B.inputs.bkw(Nv)
+    _, dv = B.inputs.velocity_axis(Nv)
+    assert abs(f.sum() * dv ** 3 - 1.0) < 1e-6      # unit mass
+    assert abs(Q.sum() * dv ** 3) < 1e-8            # collisions conserve mass
+    assert f.min() >= 0
