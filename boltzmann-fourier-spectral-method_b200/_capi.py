@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libbfsm_b200.so")
 
 BFSM_OK, BFSM_ERR_INVALID, BFSM_ERR_UNSUPPORTED, BFSM_ERR_CUDA, BFSM_ERR_NOMEM = range(5)
 BFSM_FLAG_NO_FOLD = 1
+BFSM_FLAG_NO_PACK = 2
 
 #: every symbol include/bfsm_b200.h declares
 EXPORTS = (
@@ -19,13 +20,13 @@ EXPORTS = (
     "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host",
 )
 
-KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final")
+KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final", "nyquist")
 
 
 class PlanInfo(ctypes.Structure):
     _fields_ = [
         ("n", ctypes.c_int), ("n_r", ctypes.c_int), ("n_s", ctypes.c_int),
-        ("folded", ctypes.c_int), ("pairs_total", ctypes.c_int), ("pairs_local", ctypes.c_int),
+        ("folded", ctypes.c_int), ("packed", ctypes.c_int), ("pairs_total", ctypes.c_int), ("pairs_local", ctypes.c_int),
         ("chunk_pairs", ctypes.c_int), ("launches_per_cell", ctypes.c_int),
         ("scratch_bytes", ctypes.c_longlong),
     ]

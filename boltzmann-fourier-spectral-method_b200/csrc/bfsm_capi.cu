@@ -55,6 +55,8 @@ struct bfsm_plan {
     int N = 0, n_r = 0, n_s = 0, device = 0;
     double gamma = 0, b_gamma = 0, L = 0;
     int folded = 0;
+    int packed = 1;   // Hermitian packing: one 3-D transform per pair + Nyquist-plane correction
+    int GY = 4;       // pair groups (= S partial slots) of k_nyq_accum
     int pairs_total = 0, pairs_local = 0;
     int n_r_local = 0;
     int M = 0; // |l|^2 table length
@@ -76,8 +78,10 @@ struct bfsm_plan {
     // device scratch
     cplx *fhat = nullptr;  // [N^3]
     cplx *tmp = nullptr;   // [max(2, n_r_local)][N^3]  hybrid scratch of the single-shot stages
-    cplx *hyb = nullptr;   // [2*chunk][N^3]
-    double *S = nullptr;   // [G][n_r_local][N^3]
+    cplx *hyb = nullptr;   // [(packed ? 1 : 2)*chunk][N^3]
+    double *S = nullptr;   // [G (+GY when packed)][n_r_local][N^3]
+    cplx *nyq = nullptr;   // [3][N][N] Nyquist planes of fhat (packed mode)
+    cplx *uvw = nullptr;   // [chunk][3][N][N] (packed mode)
     cplx *qhat = nullptr;  // [N^3]
     double *stage_f = nullptr, *stage_q = nullptr; // host-pointer entry point staging
     size_t stage_cells = 0;
@@ -144,12 +148,20 @@ template <int N> size_t pencil_gain_smem()
 template <int N> int configure_kernels()
 {
     using Lc = Launch<N>;
-    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>,
+    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB>,
+    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)plane_gain_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_gain_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pencil_gain_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_plane_nyq<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)plane_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, -1, PLANE_REAL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, +1, PLANE_FINAL>,
@@ -208,23 +220,50 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     }
 
     // gain: S_r = sum_sigma w Re(g1 g2)
-    CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)p->G * p->n_r_local * N3, st));
+    const int slots = p->packed ? p->G + p->GY : p->G;
+    CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)slots * p->n_r_local * N3, st));
+    if (p->packed) {
+        ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
+        k_extract_nyq<N><<<(3 * N * N + 255) / 256, 256, 0, st>>>(p->fhat, p->nyq);
+    }
     for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk) {
         const int nc = std::min(p->chunk, p->pairs_local - c0);
-        const int items = 2 * nc;
+        const int items = p->packed ? nc : 2 * nc;
         // persistent: one CTA per SM slot, never more CTAs than (plane, item-pair) units
         int ctas = std::min(p->gy, std::max(1, (N * items) / Lc::GROUPS));
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
-            k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
-                <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
-                    p->fhat, p->phase, p->tw, p->hyb, c0, items);
+            if (p->packed)
+                k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, true>
+                    <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items);
+            else
+                k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>
+                    <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items);
         }
         const int G = std::min(p->G, nc);
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
-            k_pencil_gain<N, Lc::PG, Lc::PMINB><<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
-                p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+            if (p->packed)
+                k_pencil_gain<N, Lc::PG, Lc::PMINB, true>
+                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+            else
+                k_pencil_gain<N, Lc::PG, Lc::PMINB, false>
+                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+        }
+        if (p->packed) {
+            // exact correction for the Nyquist planes: S2_r += sum_s Re(Y_s^2)
+            ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
+            k_plane_nyq<N><<<dim3(3, nc), N * Geo<N>::B, plane_smem<N>(), st>>>(
+                p->nyq, p->phase, p->pair_w, p->tw, p->uvw, c0);
+            const int GY = std::min(p->GY, nc);
+            constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
+            k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, st>>>(
+                p->uvw, p->pair_r, p->r_end, p->S + (size_t)p->G * p->n_r_local * N3, c0, nc,
+                p->n_r_local);
         }
     }
 
@@ -233,7 +272,7 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         ProfSpan ps(p, st, BFSM_KCLASS_ACCUM);
         if (p->n_r_local > 0) {
             k_plane<N, -1, PLANE_REAL><<<dim3(N, p->n_r_local), N * Geo<N>::B, plane_smem<N>(), st>>>(
-                p->S, p->G, (size_t)p->n_r_local * N3, nullptr, nullptr, nullptr, p->tw, p->tmp);
+                p->S, slots, (size_t)p->n_r_local * N3, nullptr, nullptr, nullptr, p->tw, p->tmp);
         }
         k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
     }
@@ -259,7 +298,7 @@ template <int N> int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const
 template <int N> int launches_per_cell(const bfsm_plan *p)
 {
     const int chunks = (p->pairs_local + p->chunk - 1) / p->chunk;
-    return 2 + 2 * chunks + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
+    return 2 + (p->packed ? 1 + 4 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
 }
 
 #define DISPATCH_N(p, CALL)                                           \
@@ -344,6 +383,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     p->L = L;
     p->shard_index = shard_index;
     p->shard_count = shard_count;
+    p->packed = (flags & BFSM_FLAG_NO_PACK) ? 0 : 1;
     const int N = p->N;
     const size_t N3 = (size_t)N * N * N;
 
@@ -472,10 +512,19 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bail(rc);
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
-    if ((rc = dev_alloc(p, (void **)&p->hyb, sizeof(cplx) * N3 * 2 * (size_t)p->chunk))) return bail(rc);
-    if ((rc = dev_alloc(p, (void **)&p->S,
-                        sizeof(double) * N3 * (size_t)p->G * std::max(1, p->n_r_local))))
+    p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", 4));
+    if ((rc = dev_alloc(p, (void **)&p->hyb,
+                        sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
         return bail(rc);
+    if ((rc = dev_alloc(p, (void **)&p->S,
+                        sizeof(double) * N3 * (size_t)(p->G + (p->packed ? p->GY : 0)) *
+                            std::max(1, p->n_r_local))))
+        return bail(rc);
+    if (p->packed) {
+        if ((rc = dev_alloc(p, (void **)&p->nyq, sizeof(cplx) * 3 * N * N))) return bail(rc);
+        if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 3 * N * N * (size_t)p->chunk)))
+            return bail(rc);
+    }
     if ((rc = do_configure(p))) return bail(rc);
     *out = p;
     return BFSM_OK;
@@ -503,15 +552,26 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
     int c = chunk_pairs > 0 ? chunk_pairs : dflt;
     c = std::min(c, std::max(1, p->pairs_local));
     if (c > p->chunk) {
-        // grow the hybrid scratch
-        cplx *q = nullptr;
+        // grow the per-chunk scratch
         CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaMalloc((void **)&q, sizeof(cplx) * N3 * 2 * (size_t)c));
-        for (auto &a : p->allocs)
-            if (a == (void *)p->hyb) a = q;
-        cudaFree(p->hyb);
-        p->scratch_bytes += (long long)(sizeof(cplx) * N3 * 2 * (size_t)(c - p->chunk));
-        p->hyb = q;
+        auto regrow = [&](void **slot, size_t bytes_new, size_t bytes_old) -> int {
+            void *q = nullptr;
+            CUDA_TRY(cudaMalloc(&q, bytes_new));
+            for (auto &a : p->allocs)
+                if (a == *slot) a = q;
+            cudaFree(*slot);
+            *slot = q;
+            p->scratch_bytes += (long long)bytes_new - (long long)bytes_old;
+            return BFSM_OK;
+        };
+        const size_t per = sizeof(cplx) * N3 * (p->packed ? 1 : 2);
+        int rc = regrow((void **)&p->hyb, per * c, per * p->chunk);
+        if (rc) return rc;
+        if (p->packed) {
+            const size_t pern = sizeof(cplx) * 3 * N * N;
+            rc = regrow((void **)&p->uvw, pern * c, pern * p->chunk);
+            if (rc) return rc;
+        }
     }
     p->chunk = c;
     return BFSM_OK;
@@ -524,6 +584,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->n_r = p->n_r;
     info->n_s = p->n_s;
     info->folded = p->folded;
+    info->packed = p->packed;
     info->pairs_total = p->pairs_total;
     info->pairs_local = p->pairs_local;
     info->chunk_pairs = p->chunk;

@@ -21,6 +21,16 @@
 //   * exp(i theta(l)) = ex[i] ey[j] ez[k] (theta is linear in l): three N-entry tables per pair;
 //   * beta1(r,|l|) and beta2(|l|) depend on l only through the integer |l|^2: tabulated;
 //   * 1/N^3 (a power of two, hence exact) is folded into fhat and the tables.
+//
+// PACKED mode (default; f is real, so fhat is Hermitian): write e^{i theta} = c + i s.  Then
+//   g1 = C + iD, g2 = C - iD with C = IFFT3(c fhat), D = IFFT3(s fhat), and
+//   Re(g1 g2) = Re(Z_H^2) + Re(Y^2),   Z_H = IFFT3(m_H fhat),  Y = IFFT3(n fhat)
+// with REAL multipliers m_H = c_even + s_odd, n = c_odd + s_even (even/odd under index reversal
+// l -> -l mod N).  n vanishes off the three Nyquist planes, so
+//   Y(v) = (-1)^vx U(vy,vz) + (-1)^vy V(vx,vz) + (-1)^vz W(vx,vy)
+// is assembled from three 2-D transforms per pair (k_plane_nyq) and its square is accumulated by
+// k_nyq_accum.  ONE 3-D transform per pair instead of two, exact for every real input
+// (validated against the unpacked path and the oracle with non-band-limited noise input).
 #pragma once
 #include "bfsm_fft.cuh"
 
@@ -33,11 +43,14 @@ namespace bfsm {
 // take the items of a plane alternately.
 // Shared memory: fhat plane (N*N) | GROUPS padded planes (N*ROW) | GROUPS x 2 phase slots (3N).
 // ---------------------------------------------------------------------------------------
-template <int N, int TG, int GROUPS, int MINB>
+template <int N, int TG, int GROUPS, int MINB, bool PACKED>
 __global__ void __launch_bounds__(TG *GROUPS, MINB)
 k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
              const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items)
 {
+    // item -> pair: unpacked items are (pair, array) couples, packed items are pairs
+    constexpr int ISH = PACKED ? 0 : 1;
+    constexpr int H = N / 2;
     constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
     static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -68,16 +81,16 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = fhat[(size_t)i * N * N + t];
         const int first = it_lo + g;
         if (first < it_hi && tg < 3 * N)
-            myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> 1)) * 3 * N + tg]);
+            myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> ISH)) * 3 * N + tg]);
         __syncthreads();
 
         int slot = 0;
         for (int it = first; it < it_hi; it += GROUPS, slot ^= 1) {
-            const int arr = it & 1;
+            const int arr = PACKED ? 0 : (it & 1);
             const cplx *P = myph + slot * 3 * N;
             const bool have_next = (it + GROUPS < it_hi) && (tg < 3 * N);
             cplx nxt = make_double2(0.0, 0.0);
-            if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + GROUPS) >> 1)) * 3 * N + tg]);
+            if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + GROUPS) >> ISH)) * 3 * N + tg]);
             const cplx exi = P[i];
 
             // z pass 1 with the phase-weighted load fused in (cpp:198-225):
@@ -86,14 +99,47 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             for (int u0 = 0; u0 < N * B; u0 += TG) {
                 const int u = u0 + tg;
                 const int j = u / B, b = u % B;
-                const cplx exy = cmul(exi, P[N + j]);
+                const cplx eyj = P[N + j];
+                const cplx exy = cmul(exi, eyj);
                 cplx v[A];
+                if (!PACKED) {
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    const int k = B * a + b;
-                    const cplx e = cmul(exy, P[2 * N + k]);
-                    const cplx f = fpl[j * N + k];
-                    v[a] = arr ? cmulc(f, e) : cmul(f, e);
+                    for (int a = 0; a < A; ++a) {
+                        const int k = B * a + b;
+                        const cplx e = cmul(exy, P[2 * N + k]);
+                        const cplx f = fpl[j * N + k];
+                        v[a] = arr ? cmulc(f, e) : cmul(f, e);
+                    }
+                } else if (i != H && j != H) {
+                    // interior row: E(-l) = conj(E(l)) except at the z Nyquist column k == H
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        const int k = B * a + b;
+                        const cplx ez = P[2 * N + k];
+                        const cplx e = cmul(exy, ez);
+                        double m = e.x + e.y;
+                        if (a == H / B && b == 0) { // k == H
+                            const cplx et = cmul(make_double2(exy.x, -exy.y), ez);
+                            m = 0.5 * ((e.x + e.y) + (et.x - et.y));
+                        }
+                        const cplx f = fpl[j * N + k];
+                        v[a] = make_double2(m * f.x, m * f.y);
+                    }
+                } else {
+                    // row on the x or y Nyquist plane: general even/odd split, Et = E(-l)
+                    const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
+                    const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
+                    const cplx exyt = cmul(ext, eyt);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        const int k = B * a + b;
+                        const cplx ez = P[2 * N + k];
+                        const cplx ezt = (k == H) ? ez : make_double2(ez.x, -ez.y);
+                        const cplx e = cmul(exy, ez), et = cmul(exyt, ezt);
+                        const double m = 0.5 * ((e.x + e.y) + (et.x - et.y));
+                        const cplx f = fpl[j * N + k];
+                        v[a] = make_double2(m * f.x, m * f.y);
+                    }
                 }
                 Dft<A, +1>::run(v);
                 cplx *row = buf + j * ROW;
@@ -122,7 +168,7 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 // the forward FFT).  At every change of radius r the PG partial sums are reduced through
 // shared memory in fixed order and added to S[gy][r] -- no atomics, deterministic.
 // ---------------------------------------------------------------------------------------
-template <int N, int PG, int MINB>
+template <int N, int PG, int MINB, bool PACKED>
 __global__ void __launch_bounds__(PG *Geo<N>::B *TZ, MINB)
 k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
               const int *__restrict__ pair_r, const double *__restrict__ pair_w,
@@ -157,20 +203,34 @@ k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
         int seg_end = r_end[r] - pair0;
         if (seg_end > hi) seg_end = hi;
         for (int q = p + g; q < seg_end; q += PG) {
-            const cplx *g1 = hyb + (size_t)(2 * q) * N3 + tile_off;
-            const cplx *g2 = g1 + N3;
-            x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return g1[(size_t)x * N * N + z]; });
-            x1_pass<N, +1>(sm[g][1], tw, tg, [&](int x, int z) { return g2[(size_t)x * N * N + z]; });
-            group_sync(1 + g, TGP);
             const double w = pair_w[pair0 + q];
+            if (PACKED) {
+                const cplx *zh = hyb + (size_t)q * N3 + tile_off;
+                x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return zh[(size_t)x * N * N + z]; });
+                group_sync(1 + g, TGP);
 #pragma unroll
-            for (int m = 0; m < UNITS; ++m) {
-                cplx v0[B], v1[B];
-                x2_unit<N, +1>(sm[g][0], tg, m, v0);
-                x2_unit<N, +1>(sm[g][1], tg, m, v1);
+                for (int m = 0; m < UNITS; ++m) {
+                    cplx v0[B];
+                    x2_unit<N, +1>(sm[g][0], tg, m, v0);
 #pragma unroll
-                for (int k2 = 0; k2 < B; ++k2)
-                    acc[m][k2] += w * (v0[k2].x * v1[k2].x - v0[k2].y * v1[k2].y);
+                    for (int k2 = 0; k2 < B; ++k2)
+                        acc[m][k2] += w * (v0[k2].x * v0[k2].x - v0[k2].y * v0[k2].y);
+                }
+            } else {
+                const cplx *g1 = hyb + (size_t)(2 * q) * N3 + tile_off;
+                const cplx *g2 = g1 + N3;
+                x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return g1[(size_t)x * N * N + z]; });
+                x1_pass<N, +1>(sm[g][1], tw, tg, [&](int x, int z) { return g2[(size_t)x * N * N + z]; });
+                group_sync(1 + g, TGP);
+#pragma unroll
+                for (int m = 0; m < UNITS; ++m) {
+                    cplx v0[B], v1[B];
+                    x2_unit<N, +1>(sm[g][0], tg, m, v0);
+                    x2_unit<N, +1>(sm[g][1], tg, m, v1);
+#pragma unroll
+                    for (int k2 = 0; k2 < B; ++k2)
+                        acc[m][k2] += w * (v0[k2].x * v1[k2].x - v0[k2].y * v1[k2].y);
+                }
             }
             group_sync(1 + g, TGP);
         }
@@ -370,6 +430,149 @@ k_pencil_final(const cplx *__restrict__ H, const cplx *__restrict__ twtab,
             const double fv = f[idx]; // read before the (possibly aliased) write below
             Q[idx] = v0[k2].x - v1[k2].x * fv;
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Nyquist-plane correction of the PACKED mode.
+// ---------------------------------------------------------------------------------------
+
+// nyq[q][a][b]: the three Nyquist planes of fhat, q = 0: fhat(H,a,b), 1: fhat(a,H,b), 2: fhat(a,b,H)
+template <int N>
+__global__ void k_extract_nyq(const cplx *__restrict__ fhat, cplx *__restrict__ nyq)
+{
+    constexpr int H = N / 2;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 3 * N * N) return;
+    const int q = t / (N * N), a = (t / N) % N, b = t % N;
+    const size_t src = (q == 0) ? ((size_t)H * N + a) * N + b
+                     : (q == 1) ? ((size_t)a * N + H) * N + b
+                                : ((size_t)a * N + b) * N + H;
+    nyq[t] = fhat[src];
+}
+
+// k_plane_nyq: grid (3 planes, pairs of the chunk), block N*B.  Plane q of pair p:
+//   uvw[p][q] = sqrt(w_p) * IFFT2( n(l) * fhat(l) ) over the two free axes, with
+//   n = (Re E - Re Et + Im E + Im Et)/2, Et(l) = E(-l); lines shared by two planes are
+//   counted once (plane 1 drops i == H, plane 2 drops i == H and j == H).
+template <int N>
+__global__ void __launch_bounds__(N *Geo<N>::B)
+k_plane_nyq(const cplx *__restrict__ nyq, const cplx *__restrict__ phase,
+            const double *__restrict__ pair_w, const cplx *__restrict__ twtab,
+            cplx *__restrict__ uvw, int pair0)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, TG = N * B, H = N / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *buf = reinterpret_cast<cplx *>(smem_raw);
+    const int q = blockIdx.x, pl = blockIdx.y, tg = threadIdx.x;
+    const cplx *P = phase + (size_t)(pair0 + pl) * 3 * N;
+    const cplx *src = nyq + (size_t)q * N * N;
+    const int axA = (q == 0) ? 1 : 0, axB = (q == 2) ? 1 : 2;
+    const cplx efix = __ldg(&P[q * N + H]); // Nyquist entry: e(-l) = e(l)
+    const double sw = sqrt(__ldg(&pair_w[pair0 + pl]));
+
+    cplx tw[A - 1];
+    load_twiddles<N, +1>(tw, twtab, tg % B);
+
+    z1_pass<N, +1, TG>(buf, tw, tg, [&](int a, int b) {
+        if ((q >= 1 && a == H) || (q == 2 && b == H)) return make_double2(0.0, 0.0);
+        const cplx ea = __ldg(&P[axA * N + a]), eb = __ldg(&P[axB * N + b]);
+        const cplx eat = (a == H) ? ea : make_double2(ea.x, -ea.y);
+        const cplx ebt = (b == H) ? eb : make_double2(eb.x, -eb.y);
+        const cplx e = cmul(cmul(efix, ea), eb), et = cmul(cmul(efix, eat), ebt);
+        const double n = 0.5 * sw * ((e.x - et.x) + (e.y + et.y));
+        const cplx f = src[a * N + b];
+        return make_double2(n * f.x, n * f.y);
+    });
+    __syncthreads();
+    z2_pass<N, +1, TG>(buf, tg);
+    __syncthreads();
+    y1_pass<N, +1, TG>(buf, tw, tg);
+    __syncthreads();
+    cplx *d = uvw + ((size_t)pl * 3 + q) * N * N;
+    y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { d[y * N + z] = val; });
+}
+
+// k_nyq_accum: S2_r += sum_s Re(Y_s^2), Y_s = (-1)^x U_s(y,z) + (-1)^y V_s(x,z) + (-1)^z W_s(x,y)
+// (sqrt(w_s) already folded into U,V,W).  grid (tiles of 16^3 outputs, GY); block 256 threads,
+// each owning the 2 x 2 x 4 brick x in {bx,bx+1}, y in {by,by+1}, z in {zq, zq+4, zq+8, zq+12}
+// (even bx, by: the x/y signs are compile-time; the z sign is a per-thread constant).  CTA (tile,gy)
+// covers share gy of the chunk's pairs and owns partial slot gy of S2 -- no atomics.  The next
+// pair's tile slices are fetched into registers while the current one is being consumed.
+template <int N>
+__global__ void __launch_bounds__(256)
+k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
+            const int *__restrict__ r_end, double *__restrict__ S2, int pair0, int n_pairs_chunk,
+            int n_r_local)
+{
+    constexpr int NT = 16, TPD = N / NT, PADR = NT + 2;
+    constexpr size_t N3 = (size_t)N * N * N;
+    __shared__ __align__(16) cplx sU[NT][PADR], sV[NT][PADR], sW[NT][PADR]; // [y][z], [x][z], [x][y]
+    const int t = threadIdx.x;
+    const int tx0 = (blockIdx.x / (TPD * TPD)) * NT, ty0 = ((blockIdx.x / TPD) % TPD) * NT,
+              tz0 = (blockIdx.x % TPD) * NT;
+    const int zq = t % 4, by = 2 * ((t / 4) % 8), bx = 2 * (t / 32);
+    const double sz = (zq & 1) ? -1.0 : 1.0;
+    const int la = t / NT, lb = t % NT; // element of the 16 x 16 slices this thread stages
+    const int G = gridDim.y;
+    const int lo = (int)(((long long)n_pairs_chunk * blockIdx.y) / G);
+    const int hi = (int)(((long long)n_pairs_chunk * (blockIdx.y + 1)) / G);
+
+    auto fetch = [&](int q, cplx &u, cplx &v, cplx &w) {
+        const cplx *base = uvw + (size_t)q * 3 * N * N;
+        u = base[(size_t)(ty0 + la) * N + tz0 + lb];
+        v = base[(size_t)N * N + (size_t)(tx0 + la) * N + tz0 + lb];
+        w = base[(size_t)2 * N * N + (size_t)(tx0 + la) * N + ty0 + lb];
+    };
+
+    double acc[2][2][4];
+    int p = lo;
+    while (p < hi) {
+        const int r = pair_r[pair0 + p];
+        int seg_end = r_end[r] - pair0;
+        if (seg_end > hi) seg_end = hi;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
+        cplx nu, nv, nw;
+        fetch(p, nu, nv, nw);
+        for (int q = p; q < seg_end; ++q) {
+            __syncthreads(); // previous slices fully consumed
+            sU[la][lb] = nu;
+            sV[la][lb] = nv;
+            sW[la][lb] = nw;
+            __syncthreads();
+            if (q + 1 < seg_end) fetch(q + 1, nu, nv, nw);
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const cplx w0 = sW[bx + a][by + b];
+                    // fold the x sign into everything: Y^2 is even in Y, so use (-1)^x Y
+                    const double wr = (a ? -sz : sz) * w0.x, wi = (a ? -sz : sz) * w0.y;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const cplx uu = sU[by + b][zq + 4 * c], vv = sV[bx + a][zq + 4 * c];
+                        // (-1)^x Y = U + (-1)^(x+y) V + (-1)^(x+z) W
+                        const double yr = uu.x + ((a ^ b) ? -vv.x : vv.x) + wr;
+                        const double yi = uu.y + ((a ^ b) ? -vv.y : vv.y) + wi;
+                        acc[a][b][c] = fma(yr, yr, acc[a][b][c]);
+                        acc[a][b][c] = fma(-yi, yi, acc[a][b][c]);
+                    }
+                }
+        }
+        double *Sr = S2 + ((size_t)blockIdx.y * n_r_local + r) * N3;
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b)
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    Sr[((size_t)(tx0 + bx + a) * N + ty0 + by + b) * N + tz0 + zq + 4 * c] += acc[a][b][c];
+        p = seg_end;
     }
 }
 

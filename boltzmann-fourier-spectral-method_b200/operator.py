@@ -24,7 +24,7 @@ def _torch():
 
 class BoltzmannOperatorB200:
     def __init__(self, gl_quadrature, spherical_quadrature, Nvx, Nvy, Nvz, gamma, b_gamma, L,
-                 device=None, shard_index=0, shard_count=1, fold=True):
+                 device=None, shard_index=0, shard_count=1, fold=True, pack=True):
         # like the reference constructors: store arguments only
         self.gl_quadrature = gl_quadrature
         self.spherical_quadrature = spherical_quadrature
@@ -33,6 +33,7 @@ class BoltzmannOperatorB200:
         self.device = device
         self.shard_index, self.shard_count = int(shard_index), int(shard_count)
         self.fold = bool(fold)
+        self.pack = bool(pack)
         self._plan = None
         self._lib = None
 
@@ -65,7 +66,8 @@ class BoltzmannOperatorB200:
             len(rho), rho.ctypes.data_as(dp), w_r.ctypes.data_as(dp),
             len(sx), sx.ctypes.data_as(dp), sy.ctypes.data_as(dp), sz.ctypes.data_as(dp),
             w_s.ctypes.data_as(dp), self.gamma, self.b_gamma, self.L, self.device,
-            self.shard_index, self.shard_count, 0 if self.fold else _capi.BFSM_FLAG_NO_FOLD)
+            self.shard_index, self.shard_count,
+            (0 if self.fold else _capi.BFSM_FLAG_NO_FOLD) | (0 if self.pack else _capi.BFSM_FLAG_NO_PACK))
         _capi.check(rc)
         self._plan = plan
         self._lib = lib

@@ -43,6 +43,8 @@ enum {
 
 /* plan flags */
 #define BFSM_FLAG_NO_FOLD 1u /* transform every (r,sigma) pair even if the design is antipodal */
+#define BFSM_FLAG_NO_PACK 2u /* two 3-D transforms per pair (g1 and g2) instead of the Hermitian-
+                                packed single transform + Nyquist-plane correction */
 
 typedef struct bfsm_plan bfsm_plan;
 
@@ -114,6 +116,7 @@ typedef struct {
     int n;                   /* points per axis */
     int n_r, n_s;            /* quadrature sizes as given */
     int folded;              /* 1 if antipodal folding is active */
+    int packed;              /* 1 if Hermitian packing (one transform per pair) is active */
     int pairs_total;         /* size of the (possibly folded) work list, all shards */
     int pairs_local;         /* pairs this plan transforms */
     int chunk_pairs;         /* pairs per gain-kernel launch */
@@ -135,7 +138,8 @@ enum {
     BFSM_KCLASS_PENCIL_GAIN = 2, /* k_pencil_gain : inverse FFT (x) + product + accumulate  */
     BFSM_KCLASS_ACCUM = 3,       /* k_plane<REAL> + k_pencil_accum : Qhat = sum_r ...       */
     BFSM_KCLASS_FINAL = 4,       /* k_plane<FINAL> + k_pencil_final : loss + combine        */
-    BFSM_KCLASS_COUNT = 5
+    BFSM_KCLASS_NYQUIST = 5,     /* k_extract_nyq + k_plane_nyq + k_nyq_accum (packed mode) */
+    BFSM_KCLASS_COUNT = 6
 };
 int bfsm_collide_profiled(bfsm_plan *plan, double *Q_dev, const double *f_dev, void *stream,
                           double *ms_by_class, int *launches_by_class);
