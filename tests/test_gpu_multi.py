@@ -1,0 +1,58 @@
+"""Real multi-GPU check (needs >= 2 GPUs; skipped otherwise): pair-sharded evaluation with one NCCL
+all-reduce per evaluation must reproduce the single-GPU result."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["BFSM_ROOT"]); sys.path.insert(0, os.path.join(os.environ["BFSM_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import bfsm_b200 as B
+from helpers import make_input, inp, quadrature
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+D = B.submodule("distributed")
+Nv, n_r, n_s = 32, 6, 32
+gl, sd = quadrature(n_r, n_s)
+f = torch.from_numpy(make_input("noise", Nv)).cuda().reshape(-1)
+full = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN, device=rank)
+full.initialize()
+Q_full = torch.empty_like(f); full(Q_full, f)
+shard = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN, device=rank,
+                                shard_index=rank, shard_count=world)
+shard.initialize()
+op = D.PairShardedCollision(shard, Nv ** 3)
+Q = torch.empty_like(f); op(Q, f); torch.cuda.synchronize()
+err = float((Q - Q_full).abs().max() / Q_full.abs().max())
+gathered = [torch.empty_like(Q) for _ in range(world)]
+dist.all_gather(gathered, Q)
+same = all(torch.equal(g, gathered[0]) for g in gathered)
+if rank == 0:
+    print(f"RESULT err={err:.3e} same={same} pairs_local={shard.info()['pairs_local']}")
+dist.destroy_process_group()
+'''
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_pair_sharding_over_nccl(tmp_path):
+    world = min(torch.cuda.device_count(), 8)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    env = dict(os.environ, BFSM_ROOT=ROOT)
+    out = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+         "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+        capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("RESULT")][0]
+    err = float(line.split("err=")[1].split()[0])
+    assert err <= 1e-13, line
+    assert "same=True" in line, line
