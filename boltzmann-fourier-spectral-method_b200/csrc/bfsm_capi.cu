@@ -57,6 +57,10 @@ struct bfsm_plan {
     int folded = 0;
     int packed = 1;   // Hermitian packing: one 3-D transform per pair + Nyquist-plane correction
     int GY = 4;       // pair groups (= S partial slots) of k_nyq_accum
+    int async_pencil = 1; // cp.async ring in the packed pencil kernel
+    int use_side = 1;     // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr};
     int pairs_total = 0, pairs_local = 0;
     int n_r_local = 0;
     int M = 0; // |l|^2 table length
@@ -81,7 +85,7 @@ struct bfsm_plan {
     cplx *hyb = nullptr;   // [(packed ? 1 : 2)*chunk][N^3]
     double *S = nullptr;   // [G (+GY when packed)][n_r_local][N^3]
     cplx *nyq = nullptr;   // [3][N][N] Nyquist planes of fhat (packed mode)
-    cplx *uvw = nullptr;   // [chunk][3][N][N] (packed mode)
+    cplx *uvw = nullptr;   // [2][chunk][3][N][N] (packed mode, double buffered)
     cplx *qhat = nullptr;  // [N^3]
     double *stage_f = nullptr, *stage_q = nullptr; // host-pointer entry point staging
     size_t stage_cells = 0;
@@ -129,9 +133,9 @@ int env_int(const char *name, int dflt)
 
 // ---- per-N launch geometry ------------------------------------------------------------
 template <int N> struct Launch;
-template <> struct Launch<64> { static constexpr int TG = 256, GROUPS = 2, MINB = 1, PG = 4, PMINB = 2, G = 1, CHUNK = 96; };
-template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, PMINB = 2, G = 4, CHUNK = 256; };
-template <> struct Launch<16> { static constexpr int TG = 64, GROUPS = 2, MINB = 4, PG = 8, PMINB = 2, G = 8, CHUNK = 1024; };
+template <> struct Launch<64> { static constexpr int TG = 256, GROUPS = 2, MINB = 1, PG = 4, PMINB = 2, G = 1, CHUNK = 384, PSTAGES = 3; };
+template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, PMINB = 2, G = 4, CHUNK = 256, PSTAGES = 3; };
+template <> struct Launch<16> { static constexpr int TG = 64, GROUPS = 2, MINB = 4, PG = 8, PMINB = 2, G = 8, CHUNK = 1024, PSTAGES = 3; };
 
 template <int N> size_t plane_gain_smem()
 {
@@ -145,9 +149,20 @@ template <int N> size_t pencil_gain_smem()
     return sizeof(cplx) * (size_t)Launch<N>::PG * 2 * N * TZ;
 }
 
+template <int N> size_t pencil_async_smem()
+{
+    // optional padding (tuning knob): a larger request lowers the CTAs/SM of the pencil kernel so
+    // that side-stream kernels can be co-resident
+    static const int pad = env_int("BFSM_PENCIL_SMEM_PAD", 0);
+    return sizeof(cplx) * (size_t)Launch<N>::PG * Launch<N>::PSTAGES * N * TZ + (size_t)pad;
+}
+
 template <int N> int configure_kernels()
 {
     using Lc = Launch<N>;
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pencil_async_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain_smem<N>()));
@@ -160,8 +175,7 @@ template <int N> int configure_kernels()
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_gain_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_plane_nyq<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)plane_smem<N>()));
+
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, -1, PLANE_REAL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, +1, PLANE_FINAL>,
@@ -226,9 +240,18 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
         k_extract_nyq<N><<<(3 * N * N + 255) / 256, 256, 0, st>>>(p->fhat, p->nyq);
     }
-    for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk) {
+    int ci = 0;
+    bool nyq_pending[2] = {false, false};
+    const bool side = p->packed && p->use_side && p->side;
+    for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk, ++ci) {
         const int nc = std::min(p->chunk, p->pairs_local - c0);
         const int items = p->packed ? nc : 2 * nc;
+        const int ub = ci & 1; // uvw buffer of this chunk
+        cplx *uvw = p->packed ? p->uvw + (size_t)ub * 3 * N * N * p->chunk : nullptr;
+        if (side && nyq_pending[ub]) { // k_nyq_accum of chunk ci-2 must be done with uvw[ub]
+            CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
+            nyq_pending[ub] = false;
+        }
         // persistent: one CTA per SM slot, never more CTAs than (plane, item-pair) units
         int ctas = std::min(p->gy, std::max(1, (N * items) / Lc::GROUPS));
         {
@@ -236,16 +259,41 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             if (p->packed)
                 k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, true>
                     <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items);
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
             else
                 k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>
                     <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items);
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items, nullptr, nullptr, nullptr);
+        }
+        if (p->packed) {
+            // exact correction for the Nyquist planes: S2_r += sum_s Re(Y_s^2).  FP64-only work,
+            // issued on the side stream so that it overlaps the memory-bound pencil kernel.
+            cudaStream_t ns = side ? p->side : st;
+            if (side) {
+                CUDA_TRY(cudaEventRecord(p->ev_plane[ub], st));
+                CUDA_TRY(cudaStreamWaitEvent(ns, p->ev_plane[ub], 0));
+            }
+            {
+                ProfSpan ps(p, ns, BFSM_KCLASS_NYQUIST);
+                const int GY = std::min(p->GY, nc);
+                constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
+                k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
+                    uvw, p->pair_r, p->r_end, p->S + (size_t)p->G * p->n_r_local * N3, c0, nc,
+                    p->n_r_local);
+            }
+            if (side) {
+                CUDA_TRY(cudaEventRecord(p->ev_nyq[ub], ns));
+                nyq_pending[ub] = true;
+            }
         }
         const int G = std::min(p->G, nc);
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
-            if (p->packed)
+            if (p->packed && p->async_pencil)
+                k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>
+                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+            else if (p->packed)
                 k_pencil_gain<N, Lc::PG, Lc::PMINB, true>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
@@ -254,18 +302,9 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
         }
-        if (p->packed) {
-            // exact correction for the Nyquist planes: S2_r += sum_s Re(Y_s^2)
-            ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
-            k_plane_nyq<N><<<dim3(3, nc), N * Geo<N>::B, plane_smem<N>(), st>>>(
-                p->nyq, p->phase, p->pair_w, p->tw, p->uvw, c0);
-            const int GY = std::min(p->GY, nc);
-            constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
-            k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, st>>>(
-                p->uvw, p->pair_r, p->r_end, p->S + (size_t)p->G * p->n_r_local * N3, c0, nc,
-                p->n_r_local);
-        }
     }
+    for (int ub = 0; ub < 2; ++ub)
+        if (side && nyq_pending[ub]) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
 
     // Qhat = sum_r coef_r(|l|^2) FFT3(S_r)   (cpp:249-273)
     {
@@ -298,7 +337,7 @@ template <int N> int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const
 template <int N> int launches_per_cell(const bfsm_plan *p)
 {
     const int chunks = (p->pairs_local + p->chunk - 1) / p->chunk;
-    return 2 + (p->packed ? 1 + 4 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
+    return 2 + (p->packed ? 1 + 3 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
 }
 
 #define DISPATCH_N(p, CALL)                                           \
@@ -513,6 +552,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
     p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", 4));
+    p->async_pencil = env_int("BFSM_ASYNC_PENCIL", 1);
     if ((rc = dev_alloc(p, (void **)&p->hyb,
                         sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
         return bail(rc);
@@ -522,8 +562,18 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
         return bail(rc);
     if (p->packed) {
         if ((rc = dev_alloc(p, (void **)&p->nyq, sizeof(cplx) * 3 * N * N))) return bail(rc);
-        if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 3 * N * N * (size_t)p->chunk)))
+        if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk)))
             return bail(rc);
+        p->use_side = env_int("BFSM_SIDE_STREAM", 1);
+        if (p->use_side) {
+            if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess)
+                return bail(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
+            for (int k = 0; k < 2; ++k) {
+                if (cudaEventCreateWithFlags(&p->ev_plane[k], cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&p->ev_nyq[k], cudaEventDisableTiming) != cudaSuccess)
+                    return bail(fail(BFSM_ERR_CUDA, "cudaEventCreate failed"));
+            }
+        }
     }
     if ((rc = do_configure(p))) return bail(rc);
     *out = p;
@@ -536,6 +586,11 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     GuardDevice guard(p->device);
     for (void *q : p->allocs) cudaFree(q);
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) {
+        if (p->ev_plane[k]) cudaEventDestroy(p->ev_plane[k]);
+        if (p->ev_nyq[k]) cudaEventDestroy(p->ev_nyq[k]);
+    }
+    if (p->side) cudaStreamDestroy(p->side);
     if (p->stage_f) cudaFree(p->stage_f);
     if (p->stage_q) cudaFree(p->stage_q);
     delete p;
@@ -568,7 +623,7 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
         int rc = regrow((void **)&p->hyb, per * c, per * p->chunk);
         if (rc) return rc;
         if (p->packed) {
-            const size_t pern = sizeof(cplx) * 3 * N * N;
+            const size_t pern = sizeof(cplx) * 2 * 3 * N * N;
             rc = regrow((void **)&p->uvw, pern * c, pern * p->chunk);
             if (rc) return rc;
         }

@@ -221,6 +221,34 @@ __device__ __forceinline__ int x2_unit(const cplx *sm, int tg, int m, cplx (&v)[
 // Fourier mode of index t (FFTWBoltzmannOperator.cpp:50-57): 0..N/2-1, -N/2..-1.
 template <int N> __device__ __forceinline__ int mode_of(int t) { return t < N / 2 ? t : t - N; }
 
+// x pass 1 reading its inputs from the same dense tile it writes (in place): thread (b,z)
+// reads rows B*a+b and writes rows B*k1+b -- the same set of rows, so no hazard inside the pass.
+template <int N, int SIGN>
+__device__ __forceinline__ void x1_pass_inplace(cplx *sm, const cplx (&tw)[Geo<N>::A - 1], int tg)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B;
+    const int z = tg % TZ, b = tg / TZ;
+    cplx v[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) v[a] = sm[(B * a + b) * TZ + z];
+    Dft<A, SIGN>::run(v);
+    sm[b * TZ + z] = v[0];
+#pragma unroll
+    for (int k1 = 1; k1 < A; ++k1) sm[(B * k1 + b) * TZ + z] = cmul(v[k1], tw[k1 - 1]);
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS) and its group bookkeeping
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int KEEP> __device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory");
+}
+
 __device__ __forceinline__ void group_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -46,11 +46,18 @@ namespace bfsm {
 template <int N, int TG, int GROUPS, int MINB, bool PACKED>
 __global__ void __launch_bounds__(TG *GROUPS, MINB)
 k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
-             const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items)
+             const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items,
+             const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
+             cplx *__restrict__ uvw)
 {
     // item -> pair: unpacked items are (pair, array) couples, packed items are pairs
     constexpr int ISH = PACKED ? 0 : 1;
     constexpr int H = N / 2;
+    // packed mode appends the three Nyquist planes of fhat as "planes" N, N+1, N+2: plane N+q of
+    // pair p yields uvw[p][q] = sqrt(w_p) IFFT2(n(l) fhat(l)) over the two free axes, where
+    // n = (Re E - Re Et + Im E + Im Et)/2, Et(l) = E(-l); lines shared by two planes are counted
+    // once (plane 1 drops i == H, plane 2 drops i == H and j == H).
+    constexpr int NPL = PACKED ? N + 3 : N;
     constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
     static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -66,7 +73,7 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     load_twiddles<N, +1>(tw, twtab, tg % B);
 
     // flat work list: index = plane * n_items + item; this CTA owns [w_lo, w_hi)
-    const long long total = (long long)N * n_items;
+    const long long total = (long long)NPL * n_items;
     const int w_lo = (int)((total * blockIdx.x) / gridDim.x);
     const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
 
@@ -78,7 +85,10 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         if ((long long)(i + 1) * n_items > w_hi) it_hi = w_hi - i * n_items;
 
         __syncthreads(); // every group is done with the previous plane
-        for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = fhat[(size_t)i * N * N + t];
+        {
+            const cplx *srcp = (i < N) ? fhat + (size_t)i * N * N : nyq + (size_t)(i - N) * N * N;
+            for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = srcp[t];
+        }
         const int first = it_lo + g;
         if (first < it_hi && tg < 3 * N)
             myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> ISH)) * 3 * N + tg]);
@@ -91,7 +101,16 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             const bool have_next = (it + GROUPS < it_hi) && (tg < 3 * N);
             cplx nxt = make_double2(0.0, 0.0);
             if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + GROUPS) >> ISH)) * 3 * N + tg]);
-            const cplx exi = P[i];
+            const cplx exi = P[i < N ? i : 0];
+            // Nyquist-plane items: fixed axis q, free axes (axA, axB) index rows / columns
+            const int nq = i - N;
+            const int axA = (nq == 0) ? 1 : 0, axB = (nq == 2) ? 1 : 2;
+            cplx efix = make_double2(0.0, 0.0);
+            double sw = 0.0;
+            if (PACKED && i >= N) {
+                efix = P[nq * N + H];
+                sw = 0.5 * sqrt(__ldg(&pair_w[pair0 + it]));
+            }
 
             // z pass 1 with the phase-weighted load fused in (cpp:198-225):
             // A1 = e^{i theta} fhat, A2 = e^{-i theta} fhat, theta separable in (i,j,k).
@@ -109,6 +128,22 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                         const cplx e = cmul(exy, P[2 * N + k]);
                         const cplx f = fpl[j * N + k];
                         v[a] = arr ? cmulc(f, e) : cmul(f, e);
+                    }
+                } else if (i >= N) {
+                    const cplx ea = P[axA * N + j];
+                    const cplx eat = (j == H) ? ea : make_double2(ea.x, -ea.y);
+                    const cplx fa = cmul(efix, ea), fat = cmul(efix, eat);
+                    const bool zero_row = (nq >= 1) && (j == H);
+#pragma unroll
+                    for (int a = 0; a < A; ++a) {
+                        const int k = B * a + b;
+                        const cplx eb = P[axB * N + k];
+                        const cplx ebt = (k == H) ? eb : make_double2(eb.x, -eb.y);
+                        const cplx e = cmul(fa, eb), et = cmul(fat, ebt);
+                        double n = sw * ((e.x - et.x) + (e.y + et.y));
+                        if (zero_row || (nq == 2 && k == H)) n = 0.0;
+                        const cplx f = fpl[j * N + k];
+                        v[a] = make_double2(n * f.x, n * f.y);
                     }
                 } else if (i != H && j != H) {
                     // interior row: E(-l) = conj(E(l)) except at the z Nyquist column k == H
@@ -153,7 +188,8 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             if (have_next) myph[(slot ^ 1) * 3 * N + tg] = nxt;
             y1_pass<N, +1, TG>(buf, tw, tg);
             group_sync(1 + g, TG);
-            cplx *dst = hyb + ((size_t)it * N + i) * N * N;
+            cplx *dst = (i < N) ? hyb + ((size_t)it * N + i) * N * N
+                                : uvw + ((size_t)it * 3 + nq) * N * N;
             y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { dst[y * N + z] = val; });
             group_sync(1 + g, TG);
         }
@@ -237,6 +273,112 @@ k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
         // flush this radius: fixed-order reduction over the PG groups
         __syncthreads();
         double *red = reinterpret_cast<double *>(&sm[0][0][0]); // PG*TILE doubles <= smem size
+#pragma unroll
+        for (int m = 0; m < UNITS; ++m)
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) {
+                red[g * TILE + (tg + m * TGP) * B + k2] = acc[m][k2];
+                acc[m][k2] = 0.0;
+            }
+        __syncthreads();
+        double *Sr = S + ((size_t)blockIdx.y * n_r_local + r) * N3 + tile_off;
+        for (int e = threadIdx.x; e < TILE; e += PG * TGP) {
+            const int x = e / TZ, z = e % TZ;
+            const int k1 = x % A, k2 = x / A;
+            const int src = (k1 * TZ + z) * B + k2;
+            double s = 0.0;
+#pragma unroll
+            for (int gg = 0; gg < PG; ++gg) s += red[gg * TILE + src];
+            Sr[(size_t)x * N * N + z] += s;
+        }
+        __syncthreads();
+        p = seg_end;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// k_pencil_gain_async (packed mode): same work split and flush as k_pencil_gain, but each group
+// streams its tiles through a STAGES-deep ring of shared-memory slots filled by cp.async
+// (LDGSTS), so the global loads of the next pairs are in flight while the current pair is
+// transformed.  Per pair and group: wait for the oldest slot, x pass 1 in place, x pass 2,
+// acc += w (Re^2 - Im^2); two group barriers per pair.
+// ---------------------------------------------------------------------------------------
+template <int N, int PG, int STAGES, int MINB>
+__global__ void __launch_bounds__(PG *Geo<N>::B *TZ, MINB)
+k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
+                    const int *__restrict__ pair_r, const double *__restrict__ pair_w,
+                    const int *__restrict__ r_end, double *__restrict__ S, int pair0,
+                    int n_pairs_chunk, int n_r_local)
+{
+    constexpr int A = Geo<N>::A, B = Geo<N>::B;
+    constexpr int TGP = B * TZ, UNITS = X2<N>::UNITS, TILE = N * TZ;
+    constexpr int CP_PER_THREAD = TILE / TGP; // 16-byte copies per thread and tile
+    constexpr size_t N3 = (size_t)N * N * N;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx(*ring)[STAGES][TILE] = reinterpret_cast<cplx(*)[STAGES][TILE]>(smem_raw); // [PG][STAGES][TILE]
+
+    const int g = threadIdx.x / TGP, tg = threadIdx.x % TGP;
+    const int y = blockIdx.x / (N / TZ), zg = blockIdx.x % (N / TZ);
+    const int G = gridDim.y;
+    const int lo = (int)(((long long)n_pairs_chunk * blockIdx.y) / G);
+    const int hi = (int)(((long long)n_pairs_chunk * (blockIdx.y + 1)) / G);
+
+    cplx tw[A - 1];
+    load_twiddles<N, +1>(tw, twtab, tg / TZ);
+
+    double acc[UNITS][B];
+#pragma unroll
+    for (int m = 0; m < UNITS; ++m)
+#pragma unroll
+        for (int k2 = 0; k2 < B; ++k2) acc[m][k2] = 0.0;
+
+    const size_t tile_off = (size_t)y * N + zg * TZ;
+    // tile element e = x*TZ + z  <->  global x*N*N + z; thread copies e = tg + c*TGP
+    auto issue = [&](int q, int slot) {
+        const cplx *src = hyb + (size_t)q * N3 + tile_off;
+        cplx *dst = ring[g][slot];
+#pragma unroll
+        for (int c = 0; c < CP_PER_THREAD; ++c) {
+            const int e = tg + c * TGP;
+            cp_async16(dst + e, src + (size_t)(e / TZ) * N * N + (e % TZ));
+        }
+    };
+
+    int p = lo;
+    while (p < hi) {
+        const int r = pair_r[pair0 + p];
+        int seg_end = r_end[r] - pair0;
+        if (seg_end > hi) seg_end = hi;
+        // this group's pairs: q_n = p + g + n*PG
+        const int n_mine = (seg_end - p - g + PG - 1) / PG;
+#pragma unroll
+        for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+            if (s0 < n_mine) issue(p + g + s0 * PG, s0);
+            cp_async_commit();
+        }
+        for (int n = 0; n < n_mine; ++n) {
+            const int q = p + g + n * PG;
+            cp_async_wait<STAGES - 2>();   // this thread's copies for pair n have landed
+            group_sync(1 + g, TGP);        // ... and everybody else's; slot (n-1) is free again
+            if (n + STAGES - 1 < n_mine) issue(q + (STAGES - 1) * PG, (n + STAGES - 1) % STAGES);
+            cp_async_commit();
+            cplx *sm = ring[g][n % STAGES];
+            x1_pass_inplace<N, +1>(sm, tw, tg);
+            group_sync(1 + g, TGP);
+            const double w = pair_w[pair0 + q];
+#pragma unroll
+            for (int m = 0; m < UNITS; ++m) {
+                cplx v0[B];
+                x2_unit<N, +1>(sm, tg, m, v0);
+#pragma unroll
+                for (int k2 = 0; k2 < B; ++k2)
+                    acc[m][k2] += w * (v0[k2].x * v0[k2].x - v0[k2].y * v0[k2].y);
+            }
+        }
+        cp_async_wait<0>();
+        // flush this radius: fixed-order reduction over the PG groups
+        __syncthreads();
+        double *red = reinterpret_cast<double *>(smem_raw); // PG*TILE doubles <= ring size
 #pragma unroll
         for (int m = 0; m < UNITS; ++m)
 #pragma unroll
@@ -451,48 +593,6 @@ __global__ void k_extract_nyq(const cplx *__restrict__ fhat, cplx *__restrict__ 
     nyq[t] = fhat[src];
 }
 
-// k_plane_nyq: grid (3 planes, pairs of the chunk), block N*B.  Plane q of pair p:
-//   uvw[p][q] = sqrt(w_p) * IFFT2( n(l) * fhat(l) ) over the two free axes, with
-//   n = (Re E - Re Et + Im E + Im Et)/2, Et(l) = E(-l); lines shared by two planes are
-//   counted once (plane 1 drops i == H, plane 2 drops i == H and j == H).
-template <int N>
-__global__ void __launch_bounds__(N *Geo<N>::B)
-k_plane_nyq(const cplx *__restrict__ nyq, const cplx *__restrict__ phase,
-            const double *__restrict__ pair_w, const cplx *__restrict__ twtab,
-            cplx *__restrict__ uvw, int pair0)
-{
-    constexpr int A = Geo<N>::A, B = Geo<N>::B, TG = N * B, H = N / 2;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx *buf = reinterpret_cast<cplx *>(smem_raw);
-    const int q = blockIdx.x, pl = blockIdx.y, tg = threadIdx.x;
-    const cplx *P = phase + (size_t)(pair0 + pl) * 3 * N;
-    const cplx *src = nyq + (size_t)q * N * N;
-    const int axA = (q == 0) ? 1 : 0, axB = (q == 2) ? 1 : 2;
-    const cplx efix = __ldg(&P[q * N + H]); // Nyquist entry: e(-l) = e(l)
-    const double sw = sqrt(__ldg(&pair_w[pair0 + pl]));
-
-    cplx tw[A - 1];
-    load_twiddles<N, +1>(tw, twtab, tg % B);
-
-    z1_pass<N, +1, TG>(buf, tw, tg, [&](int a, int b) {
-        if ((q >= 1 && a == H) || (q == 2 && b == H)) return make_double2(0.0, 0.0);
-        const cplx ea = __ldg(&P[axA * N + a]), eb = __ldg(&P[axB * N + b]);
-        const cplx eat = (a == H) ? ea : make_double2(ea.x, -ea.y);
-        const cplx ebt = (b == H) ? eb : make_double2(eb.x, -eb.y);
-        const cplx e = cmul(cmul(efix, ea), eb), et = cmul(cmul(efix, eat), ebt);
-        const double n = 0.5 * sw * ((e.x - et.x) + (e.y + et.y));
-        const cplx f = src[a * N + b];
-        return make_double2(n * f.x, n * f.y);
-    });
-    __syncthreads();
-    z2_pass<N, +1, TG>(buf, tg);
-    __syncthreads();
-    y1_pass<N, +1, TG>(buf, tw, tg);
-    __syncthreads();
-    cplx *d = uvw + ((size_t)pl * 3 + q) * N * N;
-    y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { d[y * N + z] = val; });
-}
-
 // k_nyq_accum: S2_r += sum_s Re(Y_s^2), Y_s = (-1)^x U_s(y,z) + (-1)^y V_s(x,z) + (-1)^z W_s(x,y)
 // (sqrt(w_s) already folded into U,V,W).  grid (tiles of 16^3 outputs, GY); block 256 threads,
 // each owning the 2 x 2 x 4 brick x in {bx,bx+1}, y in {by,by+1}, z in {zq, zq+4, zq+8, zq+12}
@@ -500,7 +600,7 @@ k_plane_nyq(const cplx *__restrict__ nyq, const cplx *__restrict__ phase,
 // covers share gy of the chunk's pairs and owns partial slot gy of S2 -- no atomics.  The next
 // pair's tile slices are fetched into registers while the current one is being consumed.
 template <int N>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
             const int *__restrict__ r_end, double *__restrict__ S2, int pair0, int n_pairs_chunk,
             int n_r_local)

@@ -30,10 +30,8 @@ def run(Nv, n_r, n_s, chunk, gy=None, reps=2):
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "64"
     if which == "64":
-        for chunk in (8, 16, 24, 32, 48, 96):
+        for chunk in (16, 48, 96, 192, 384):
             run(64, 8, 192, chunk)
-        for ctas in (128, 148, 296):
-            run(64, 8, 192, 24, ctas)
     elif which == "32":
         for chunk in (16, 32, 64, 128, 256):
             run(32, 16, 32, chunk)
