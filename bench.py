@@ -243,13 +243,19 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(warmup):
-        step()
-    barrier()
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    t_spin = time.perf_counter()
+    for _ in range(warmup):
+        step()
+    # keep the GPU under load for >= 0.6 s before timing so that nvidia-smi (100 ms period)
+    # reports clocks under load and the SM clock has settled (untimed)
+    while time.perf_counter() - t_spin < 0.6:
+        step()
+        torch.cuda.synchronize()
+    barrier()
+
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(steps)]
     barrier()
@@ -302,11 +308,13 @@ def run_b200(args):
         peaks, peak_src = measured_peaks()
         pairs, chunk = info["pairs_local"], info["chunk_pairs"]
         n_launch = (pairs + chunk - 1) // chunk
-        # algorithmic bytes per evaluation of each gain kernel (DESIGN.md "Kernels"):
-        #   k_plane_gain : read fhat once per launch, write both hybrid arrays of every pair
-        #   k_pencil_gain: read both hybrid arrays of every pair, read+write S_r once per launch
-        bytes_plane = 16 * N3 * (2 * pairs + n_launch)
-        bytes_pencil = 16 * N3 * (2 * pairs) + 16 * N3 * n_launch
+        arrays = 1 if info["packed"] else 2      # 3-D arrays transformed per pair
+        # algorithmic bytes per evaluation of each gain kernel:
+        #   k_plane_gain : read fhat once per launch, write `arrays` hybrid grids per pair
+        #                  (+ the three Nyquist planes per pair in packed mode)
+        #   k_pencil_gain: read `arrays` hybrid grids per pair, read+write S_r once per launch
+        bytes_plane = 16 * N3 * (arrays * pairs + n_launch) + (16 * 3 * Nv * Nv * pairs if info["packed"] else 0)
+        bytes_pencil = 16 * N3 * (arrays * pairs) + 16 * N3 * n_launch
         cls = "plane_gain" if prof["plane_gain"][0] >= prof["pencil_gain"][0] else "pencil_gain"
         ms, launches = prof[cls]
         bytes_cls = bytes_plane if cls == "plane_gain" else bytes_pencil
@@ -321,9 +329,15 @@ def run_b200(args):
             "bytes_per_launch": bytes_cls / launches, "ms_per_launch": ms / launches,
             "launches_per_eval": launches, "share_of_step": ms / total_prof_ms,
             "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
-            "note": "hybrid scratch is sized to stay L2-resident, so DRAM traffic is far below the "
-                    "algorithmic bytes (see profiles/); frac is algorithmic bytes / time over the "
-                    "HBM copy peak",
+            "note": "whole-radius chunks: the hybrid scratch (chunk x 4 MiB at 64^3) streams through "
+                    "HBM, k_plane_gain writes it and k_pencil_gain reads it back; ncu: k_plane_gain is "
+                    "shared-memory-pipe bound (68 % l1tex data pipe, 43 % FP64 pipe), k_pencil_gain "
+                    "HBM bound (see profiles/)",
+            "pipeline_hbm": {
+                "bytes_per_eval": bytes_plane + bytes_pencil,
+                "achieved_gbs": (bytes_plane + bytes_pencil) * value / 1e9,
+                "frac": (bytes_plane + bytes_pencil) * value / 1e9 / peaks["hbm_gbs"],
+                "what": "algorithmic bytes of both gain kernels per evaluation x evals/s (whole step)"},
             "survey_contract": {
                 "bytes_per_eval": contract_bytes, "P_done": info["pairs_total"],
                 "folded": bool(info["folded"]),
@@ -345,7 +359,8 @@ def run_b200(args):
             "config": {
                 "workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
                 "input": "maxmix(seed=1234)", "pairs_transformed": info["pairs_total"],
-                "antipodal_folding": bool(info["folded"]), "chunk_pairs": info["chunk_pairs"],
+                "antipodal_folding": bool(info["folded"]), "hermitian_packing": bool(info["packed"]),
+                "chunk_pairs": info["chunk_pairs"],
                 "parallelism": f"pair-shard x{world}" if world > 1 else "single GPU",
                 "l2_flush": "256 MiB written between steps (untimed); each evaluation streams "
                             ">> 126 MB through L2",

@@ -551,7 +551,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bail(rc);
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
-    p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", 4));
+    p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", N == 64 ? 4 : (N == 32 ? 24 : 64)));
     p->async_pencil = env_int("BFSM_ASYNC_PENCIL", 1);
     if ((rc = dev_alloc(p, (void **)&p->hyb,
                         sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
