@@ -249,11 +249,17 @@ def run_b200(args):
     t_spin = time.perf_counter()
     for _ in range(warmup):
         step()
-    # keep the GPU under load for >= 0.6 s before timing so that nvidia-smi (100 ms period)
-    # reports clocks under load and the SM clock has settled (untimed)
-    while time.perf_counter() - t_spin < 0.6:
+    barrier()
+    # Keep the GPU under load for >= 0.6 s before timing so that nvidia-smi (100 ms period) reports
+    # clocks under load (untimed).  The iteration count is decided on rank 0 and broadcast: every
+    # step contains a collective when world > 1, so all ranks must run the same number of steps.
+    per_step = max((time.perf_counter() - t_spin) / warmup, 1e-4)
+    n_extra = torch.tensor([int(min(2000, max(0, (0.6 - per_step * warmup) / per_step)))],
+                           dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(n_extra, src=0)
+    for _ in range(int(n_extra.item())):
         step()
-        torch.cuda.synchronize()
     barrier()
 
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
