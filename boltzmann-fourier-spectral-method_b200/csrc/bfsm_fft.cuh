@@ -80,6 +80,42 @@ template <int SIGN> struct Dft<8, SIGN> {
     }
 };
 
+// Radix-16 as 4 x 4 with compile-time W16 twiddles.  The result is left TRANSPOSED:
+// X[k1 + 4*k2] is in v[4*k1 + k2]; use dft16_reg(K) to find the register of frequency K.
+__host__ __device__ constexpr int dft16_reg(int K) { return 4 * (K % 4) + K / 4; }
+
+template <int SIGN> struct Dft<16, SIGN> {
+    static __device__ __forceinline__ cplx mulw(cplx a, double wr, double wi)
+    {
+        return make_double2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    }
+    static __device__ __forceinline__ void run(cplx (&v)[16])
+    {
+        constexpr double s = (double)SIGN;
+        constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
+        constexpr double h = 0.70710678118654752440;
+        // pass 1: radix-4 over a for each residue b (elements v[4a+b]); y[k1][b] -> v[4*k1+b]
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dft4<SIGN>(v[b], v[4 + b], v[8 + b], v[12 + b]);
+        // twiddles W16^(b*k1)
+        v[4 * 1 + 1] = mulw(v[4 * 1 + 1], c1, s * s1);                                   // W^1
+        v[4 * 1 + 2] = make_double2((v[6].x - s * v[6].y) * h, (v[6].y + s * v[6].x) * h); // W^2
+        v[4 * 1 + 3] = mulw(v[4 * 1 + 3], s1, s * c1);                                   // W^3
+        v[4 * 2 + 1] = make_double2((v[9].x - s * v[9].y) * h, (v[9].y + s * v[9].x) * h); // W^2
+        v[4 * 2 + 2] = mul_si<SIGN>(v[4 * 2 + 2]);                                       // W^4
+        v[4 * 2 + 3] = make_double2((-v[11].x - s * v[11].y) * h, (-v[11].y + s * v[11].x) * h); // W^6
+        v[4 * 3 + 1] = mulw(v[4 * 3 + 1], s1, s * c1);                                   // W^3
+        v[4 * 3 + 2] = make_double2((-v[14].x - s * v[14].y) * h, (-v[14].y + s * v[14].x) * h); // W^6
+        v[4 * 3 + 3] = mulw(v[4 * 3 + 3], -c1, -s * s1);                                 // W^9
+        // pass 2: radix-4 over b for each k1; X[k1 + 4*k2] -> v[4*k1 + k2]
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) dft4<SIGN>(v[4 * k1], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+    }
+};
+
+// Register holding frequency K after Dft<R>::run (natural for R = 4, 8; transposed for 16).
+template <int R> __host__ __device__ constexpr int dft_reg(int K) { return R == 16 ? dft16_reg(K) : K; }
+
 // Pass-1 twiddles of the calling thread: tw[k1-1] = W_N^(SIGN*b*k1), k1 = 1..A-1.
 // twtab[t] = exp(+2 pi i t / N), t in [0,N), tabulated on the host in long double.
 template <int N, int SIGN>

@@ -198,6 +198,195 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 }
 
 // ---------------------------------------------------------------------------------------
+// k_plane_gain3 (packed mode): same persistent work split as k_plane_gain, but the (y,z) plane
+// transform uses THREE register stages and only TWO shared-memory exchanges (N = 4*R):
+//   S1  thread (row j, residue b):   radix-R along z over k = 4a+b, phase-weighted load fused in
+//   S2  thread (k1, row residue b'): 4x4 block -- z twiddle W_N^(b k1), radix-4 along z (b),
+//                                    radix-4 along y (rows R a'+b'), y twiddle W_N^(b' k1')
+//   S3  thread (k1', column slot):   radix-R along y over rows R k1'+b', natural-order store
+// Column k1 + R*k2 of a row holds natural z (S1 writes residue b of frequency k1 to column
+// k1 + R*b); row R*k1'+b' feeds natural y = k1' + 4*k2'.  Rows have pitch N+1 elements (== 16 bytes
+// mod 128); S1 and S2 map consecutive lanes to consecutive rows, S3 to consecutive columns, so all
+// 16-byte accesses are bank-conflict free, global stores are contiguous per quarter-warp, and the
+// z phase table is read as a warp broadcast.  Per element: 5 shared-memory accesses + 1 global
+// store (the 4-pass version needs 8 + 1).
+// ---------------------------------------------------------------------------------------
+template <int N, int GROUPS, int MINB>
+__global__ void __launch_bounds__(4 * N *GROUPS, MINB)
+k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
+              const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items,
+              const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
+              cplx *__restrict__ uvw)
+{
+    constexpr int R = N / 4, TG = 4 * N, PITCH = N + 1, H = N / 2, NPL = N + 3;
+    static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx *fpl = reinterpret_cast<cplx *>(smem_raw);          // N x PITCH
+    cplx *bufs = fpl + N * PITCH;                             // GROUPS x (N x PITCH)
+    cplx *phs = bufs + GROUPS * N * PITCH;                    // GROUPS x 2 x 3N
+
+    const int g = threadIdx.x / TG, tg = threadIdx.x % TG;
+    cplx *buf = bufs + g * N * PITCH;
+    cplx *myph = phs + g * 2 * 3 * N;
+
+    // S1 role: row j1, residue b1.  S2 role: k1 = s2k, b' = s2b (threads < R*R).  S3: slot, k1'.
+    const int j1 = tg % N, b1 = tg / N;
+    const int s2b = tg % R, s2k = (tg / R) % R;
+    const bool s2_active = tg < R * R;
+    const int s3slot = tg % N, s3k = tg / N;
+
+    // S2 twiddles: wz[b-1] = W_N^(b*k1), wy[k-1] = W_N^(b'*k), b,k = 1..3 (inverse transform: +)
+    cplx wz[3], wy[3];
+#pragma unroll
+    for (int m = 1; m < 4; ++m) {
+        wz[m - 1] = __ldg(&twtab[(m * s2k) & (N - 1)]);
+        wy[m - 1] = __ldg(&twtab[(m * s2b) & (N - 1)]);
+    }
+
+    const long long total = (long long)NPL * n_items;
+    const int w_lo = (int)((total * blockIdx.x) / gridDim.x);
+    const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
+
+    int w = w_lo;
+    while (w < w_hi) {
+        const int i = w / n_items;
+        const int it_lo = w - i * n_items;
+        int it_hi = n_items;
+        if ((long long)(i + 1) * n_items > w_hi) it_hi = w_hi - i * n_items;
+
+        __syncthreads();
+        {
+            const cplx *srcp = (i < N) ? fhat + (size_t)i * N * N : nyq + (size_t)(i - N) * N * N;
+            for (int t = threadIdx.x; t < N * N; t += TG * GROUPS)
+                fpl[(t / N) * PITCH + (t % N)] = srcp[t];
+        }
+        const int first = it_lo + g;
+        if (first < it_hi && tg < 3 * N)
+            myph[tg] = __ldg(&phase[(size_t)(pair0 + first) * 3 * N + tg]);
+        __syncthreads();
+
+        int slot = 0;
+        for (int it = first; it < it_hi; it += GROUPS, slot ^= 1) {
+            const cplx *P = myph + slot * 3 * N;
+            const bool have_next = (it + GROUPS < it_hi) && (tg < 3 * N);
+            cplx nxt = make_double2(0.0, 0.0);
+            if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + it + GROUPS) * 3 * N + tg]);
+
+            // ---------------- S1: phase-weighted load + radix-R along z
+            {
+                const int j = j1, b = b1;
+                cplx v[R];
+                const cplx *frow = fpl + j * PITCH;
+                if (i < N) {
+                    const cplx exi = P[i], eyj = P[N + j];
+                    const cplx exy = cmul(exi, eyj);
+                    if (i != H && j != H) {
+                        // interior row: E(-l) = conj(E(l)) except at the z Nyquist column k == H
+#pragma unroll
+                        for (int a = 0; a < R; ++a) {
+                            const int k = 4 * a + b;
+                            const cplx ez = P[2 * N + k];
+                            const cplx e = cmul(exy, ez);
+                            double m = e.x + e.y;
+                            if (a == R / 2 && b == 0) { // k == H
+                                const cplx et = cmul(make_double2(exy.x, -exy.y), ez);
+                                m = 0.5 * ((e.x + e.y) + (et.x - et.y));
+                            }
+                            const cplx f = frow[k];
+                            v[a] = make_double2(m * f.x, m * f.y);
+                        }
+                    } else {
+                        const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
+                        const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
+                        const cplx exyt = cmul(ext, eyt);
+#pragma unroll
+                        for (int a = 0; a < R; ++a) {
+                            const int k = 4 * a + b;
+                            const cplx ez = P[2 * N + k];
+                            const cplx ezt = (k == H) ? ez : make_double2(ez.x, -ez.y);
+                            const cplx e = cmul(exy, ez), et = cmul(exyt, ezt);
+                            const double m = 0.5 * ((e.x + e.y) + (et.x - et.y));
+                            const cplx f = frow[k];
+                            v[a] = make_double2(m * f.x, m * f.y);
+                        }
+                    }
+                } else {
+                    // Nyquist plane q = i - N: fixed axis q, free axes (axA rows, axB columns)
+                    const int nq = i - N;
+                    const int axA = (nq == 0) ? 1 : 0, axB = (nq == 2) ? 1 : 2;
+                    const cplx efix = P[nq * N + H];
+                    const double sw = 0.5 * sqrt(__ldg(&pair_w[pair0 + it]));
+                    const cplx ea = P[axA * N + j];
+                    const cplx eat = (j == H) ? ea : make_double2(ea.x, -ea.y);
+                    const cplx fa = cmul(efix, ea), fat = cmul(efix, eat);
+                    const bool zero_row = (nq >= 1) && (j == H);
+#pragma unroll
+                    for (int a = 0; a < R; ++a) {
+                        const int k = 4 * a + b;
+                        const cplx eb = P[axB * N + k];
+                        const cplx ebt = (k == H) ? eb : make_double2(eb.x, -eb.y);
+                        const cplx e = cmul(fa, eb), et = cmul(fat, ebt);
+                        double n = sw * ((e.x - et.x) + (e.y + et.y));
+                        if (zero_row || (nq == 2 && k == H)) n = 0.0;
+                        const cplx f = frow[k];
+                        v[a] = make_double2(n * f.x, n * f.y);
+                    }
+                }
+                Dft<R, +1>::run(v);
+                cplx *row = buf + j * PITCH + R * b;
+#pragma unroll
+                for (int k1 = 0; k1 < R; ++k1) row[k1] = v[dft_reg<R>(k1)];
+            }
+            group_sync(1 + g, TG);
+            if (have_next) myph[(slot ^ 1) * 3 * N + tg] = nxt;
+
+            // ---------------- S2: 4 x 4 block, z twiddle + radix-4 (z), radix-4 (y) + y twiddle
+            if (s2_active) {
+                cplx e[4][4]; // [a' (row R a'+b')][b (column k1 + R b)]
+                cplx *blk = buf + s2b * PITCH + s2k;
+#pragma unroll
+                for (int ap = 0; ap < 4; ++ap)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) e[ap][b] = blk[(R * ap) * PITCH + R * b];
+#pragma unroll
+                for (int ap = 0; ap < 4; ++ap) {
+#pragma unroll
+                    for (int b = 1; b < 4; ++b) e[ap][b] = cmul(e[ap][b], wz[b - 1]);
+                    dft4<+1>(e[ap][0], e[ap][1], e[ap][2], e[ap][3]); // -> z = k1 + R*k2 in e[ap][k2]
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    dft4<+1>(e[0][c], e[1][c], e[2][c], e[3][c]);     // -> k1' in e[k1'][c]
+#pragma unroll
+                    for (int kp = 1; kp < 4; ++kp) e[kp][c] = cmul(e[kp][c], wy[kp - 1]);
+                }
+#pragma unroll
+                for (int kp = 0; kp < 4; ++kp)
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) blk[(R * kp) * PITCH + R * c] = e[kp][c];
+            }
+            group_sync(1 + g, TG);
+
+            // ---------------- S3: radix-R along y, natural-order store
+            {
+                cplx v[R];
+                const cplx *col = buf + (R * s3k) * PITCH + s3slot;
+#pragma unroll
+                for (int bp = 0; bp < R; ++bp) v[bp] = col[bp * PITCH];
+                Dft<R, +1>::run(v);
+                const int z = s3slot; // columns are in natural z order
+                cplx *dst = (i < N) ? hyb + ((size_t)it * N + i) * N * N
+                                    : uvw + ((size_t)it * 3 + (i - N)) * N * N;
+#pragma unroll
+                for (int k2 = 0; k2 < R; ++k2) dst[(s3k + 4 * k2) * N + z] = v[dft_reg<R>(k2)];
+            }
+            group_sync(1 + g, TG);
+        }
+        w = i * n_items + it_hi;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // k_pencil_gain: grid (N*N/TZ tiles, G), block PG*(B*TZ).  CTA (tile, gy) owns chunk pairs
 // [lo,hi) = share gy of the chunk; its PG groups take them round-robin.  Each group:
 // inverse x-FFT of g1' and g2' pencils, acc += w * Re(g1 g2) (cpp:233-246 + linearity of
