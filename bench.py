@@ -327,18 +327,31 @@ def run_b200(args):
         achieved = bytes_cls / (ms * 1e-3) / 1e9
         total_prof_ms = sum(v[0] for v in prof.values())
         contract_bytes = 96 * N3 * info["pairs_total"] + 128 * N3
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
+        # (profiles/r01_ncu_summary.json), per launch, scaled to this run's pairs per launch
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as fh:
+                cap = json.load(fh)["full_capture_k_plane_gain3"]
+            if cls == "plane_gain" and info["packed"] and Nv == 64:
+                per_pair = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["pairs_in_launch"]
+                traffic = per_pair * pairs / launches
+        except Exception:
+            traffic = None
         roofline = {
             "bound": "hbm", "kernel": "k_" + cls, "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
             "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
             else "fallback 6.65 TB/s (B200_PROFILING.md)",
             "bytes_per_launch": bytes_cls / launches, "ms_per_launch": ms / launches,
             "launches_per_eval": launches, "share_of_step": ms / total_prof_ms,
             "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
-            "note": "whole-radius chunks: the hybrid scratch (chunk x 4 MiB at 64^3) streams through "
-                    "HBM, k_plane_gain writes it and k_pencil_gain reads it back; ncu: k_plane_gain is "
-                    "shared-memory-pipe bound (68 % l1tex data pipe, 43 % FP64 pipe), k_pencil_gain "
-                    "HBM bound (see profiles/)",
+            "note": "large chunks: the hybrid scratch (chunk x 4 MiB at 64^3) streams through HBM, "
+                    "the plane kernel writes it and the pencil kernel reads it back (ncu DRAM bytes == "
+                    "algorithmic bytes).  ncu on the plane kernel: FP64 pipe 49 %, l1tex data pipe 57 %, "
+                    "16 warps/SM (128 regs x 512 threads), top stalls barrier/short_scoreboard/"
+                    "math_pipe_throttle -> latency bound at register-limited occupancy; the pencil "
+                    "kernel reads at ~5.5 TB/s (HBM bound). See profiles/r01_ncu_summary.json",
             "pipeline_hbm": {
                 "bytes_per_eval": bytes_plane + bytes_pencil,
                 "achieved_gbs": (bytes_plane + bytes_pencil) * value / 1e9,
