@@ -226,3 +226,37 @@ def test_cpp_driver_reproduces_known_answer():
     assert abs(vals["L2 error"] - 1.01189917e-04) <= 1e-7 * 1.01189917e-04
     assert abs(vals["Linf error"] - 4.25120273e-05) <= 1e-7 * 4.25120273e-05
     assert "Run statistics for B200" in out.stdout
+
+
+def test_bkw_time_integration_matches_oracle_driven_integrator(port_oracle):
+    """BASELINE config 3 (caller side): RK4 on the device against the same integrator driven by the
+    CPU oracle (16^3, a few steps), and against the exact BKW solution."""
+    I = B.submodule("integrate")
+    Nv, n_r, n_s = 16, 8, 12
+    op, gl, sd = make_operator(Nv, n_r, n_s)
+    args = oracle_args(gl, sd)
+    t0, t1, dt = 5.6, 5.9, 0.1
+    f0 = I.bkw_exact(Nv, t0)
+    f_dev = torch.from_numpy(f0.copy()).cuda().reshape(-1)
+    f_dev, steps, evals = I.rk4_torch(op, f_dev, t0, t1, dt)
+    torch.cuda.synchronize()
+    f_cpu, steps_c, _ = I.rk4_numpy(lambda x: port_oracle.collide((Nv,) * 3, *args, x), f0.copy(), t0, t1, dt)
+    assert steps == steps_c == 3 and evals == 12
+    assert rel_linf(f_dev.cpu().numpy(), f_cpu) <= REL_LINF_TOL
+
+
+def test_bkw_relaxation_error_vs_exact_solution():
+    """32^3, N_r = 32, 48-point design (cfg 3): after integrating 5.5 -> 6.5 the solution stays
+    within the spatial-discretisation error of the exact BKW solution and conserves mass."""
+    I = B.submodule("integrate")
+    Nv = 32
+    op, _, _ = make_operator(Nv, 32, 48)
+    f = torch.from_numpy(I.bkw_exact(Nv, 5.5)).cuda().reshape(-1)
+    f, steps, _ = I.rk4_torch(op, f, 5.5, 6.5, 0.05)
+    torch.cuda.synchronize()
+    exact = I.bkw_exact(Nv, 6.5)
+    l1, l2, linf = inp.error_norms(f.cpu().numpy(), exact, Nv)
+    assert steps == 20
+    assert linf / np.abs(exact).max() < 2e-3
+    _, dv = inp.velocity_axis(Nv)
+    assert abs(float(f.sum().item()) * dv ** 3 - 1.0) < 1e-5
