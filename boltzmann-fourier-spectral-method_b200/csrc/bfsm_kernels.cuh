@@ -786,17 +786,17 @@ __global__ void k_extract_nyq(const cplx *__restrict__ fhat, cplx *__restrict__ 
 // (sqrt(w_s) already folded into U,V,W).  grid (tiles of 16^3 outputs, GY); block 256 threads,
 // each owning the 2 x 2 x 4 brick x in {bx,bx+1}, y in {by,by+1}, z in {zq, zq+4, zq+8, zq+12}
 // (even bx, by: the x/y signs are compile-time; the z sign is a per-thread constant).  CTA (tile,gy)
-// covers share gy of the chunk's pairs and owns partial slot gy of S2 -- no atomics.  The next
-// pair's tile slices are fetched into registers while the current one is being consumed.
+// covers share gy of the chunk's pairs and owns partial slot gy of S2 -- no atomics.  The 16 x 16
+// slices of U, V, W stream through a 3-stage cp.async ring: one barrier per pair.
 template <int N>
 __global__ void __launch_bounds__(256, 2)
 k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
             const int *__restrict__ r_end, double *__restrict__ S2, int pair0, int n_pairs_chunk,
             int n_r_local)
 {
-    constexpr int NT = 16, TPD = N / NT, PADR = NT + 2;
+    constexpr int NT = 16, TPD = N / NT, PADR = NT + 2, STAGES = 3;
     constexpr size_t N3 = (size_t)N * N * N;
-    __shared__ __align__(16) cplx sU[NT][PADR], sV[NT][PADR], sW[NT][PADR]; // [y][z], [x][z], [x][y]
+    __shared__ __align__(16) cplx ring[STAGES][3][NT][PADR]; // [stage][U|V|W][row][col]
     const int t = threadIdx.x;
     const int tx0 = (blockIdx.x / (TPD * TPD)) * NT, ty0 = ((blockIdx.x / TPD) % TPD) * NT,
               tz0 = (blockIdx.x % TPD) * NT;
@@ -807,11 +807,12 @@ k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
     const int lo = (int)(((long long)n_pairs_chunk * blockIdx.y) / G);
     const int hi = (int)(((long long)n_pairs_chunk * (blockIdx.y + 1)) / G);
 
-    auto fetch = [&](int q, cplx &u, cplx &v, cplx &w) {
+    // U[y][z], V[x][z], W[x][y] tiles of pair q -> ring slot
+    auto issue = [&](int q, int slot) {
         const cplx *base = uvw + (size_t)q * 3 * N * N;
-        u = base[(size_t)(ty0 + la) * N + tz0 + lb];
-        v = base[(size_t)N * N + (size_t)(tx0 + la) * N + tz0 + lb];
-        w = base[(size_t)2 * N * N + (size_t)(tx0 + la) * N + ty0 + lb];
+        cp_async16(&ring[slot][0][la][lb], base + (size_t)(ty0 + la) * N + tz0 + lb);
+        cp_async16(&ring[slot][1][la][lb], base + (size_t)N * N + (size_t)(tx0 + la) * N + tz0 + lb);
+        cp_async16(&ring[slot][2][la][lb], base + (size_t)2 * N * N + (size_t)(tx0 + la) * N + ty0 + lb);
     };
 
     double acc[2][2][4];
@@ -826,15 +827,21 @@ k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
             for (int b = 0; b < 2; ++b)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
-        cplx nu, nv, nw;
-        fetch(p, nu, nv, nw);
-        for (int q = p; q < seg_end; ++q) {
-            __syncthreads(); // previous slices fully consumed
-            sU[la][lb] = nu;
-            sV[la][lb] = nv;
-            sW[la][lb] = nw;
-            __syncthreads();
-            if (q + 1 < seg_end) fetch(q + 1, nu, nv, nw);
+        const int n_mine = seg_end - p;
+        __syncthreads(); // ring free (previous segment fully consumed)
+#pragma unroll
+        for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+            if (s0 < n_mine) issue(p + s0, s0);
+            cp_async_commit();
+        }
+        for (int n = 0; n < n_mine; ++n) {
+            cp_async_wait<STAGES - 2>();
+            __syncthreads(); // pair n landed for everybody; slot of pair n-1 is free again
+            if (n + STAGES - 1 < n_mine) issue(p + n + STAGES - 1, (n + STAGES - 1) % STAGES);
+            cp_async_commit();
+            const cplx(*sU)[PADR] = ring[n % STAGES][0];
+            const cplx(*sV)[PADR] = ring[n % STAGES][1];
+            const cplx(*sW)[PADR] = ring[n % STAGES][2];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -853,6 +860,7 @@ k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
                     }
                 }
         }
+        cp_async_wait<0>();
         double *Sr = S2 + ((size_t)blockIdx.y * n_r_local + r) * N3;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
