@@ -325,7 +325,9 @@ def run_b200(args):
         ms, launches = prof[cls]
         bytes_cls = bytes_plane if cls == "plane_gain" else bytes_pencil
         achieved = bytes_cls / (ms * 1e-3) / 1e9
-        total_prof_ms = sum(v[0] for v in prof.values())
+        kernel_name = {("plane_gain", 1): "k_plane_gain3", ("plane_gain", 0): "k_plane_gain",
+                       ("pencil_gain", 1): "k_pencil_gain_async", ("pencil_gain", 0): "k_pencil_gain"}[
+                           (cls, int(bool(info["packed"])))]
         contract_bytes = 96 * N3 * info["pairs_total"] + 128 * N3
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
         # (profiles/r01_ncu_summary.json), per launch, scaled to this run's pairs per launch
@@ -339,12 +341,15 @@ def run_b200(args):
         except Exception:
             traffic = None
         roofline = {
-            "bound": "hbm", "kernel": "k_" + cls, "achieved": achieved, "peak": peaks["hbm_gbs"],
+            "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
             "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
             else "fallback 6.65 TB/s (B200_PROFILING.md)",
             "bytes_per_launch": bytes_cls / launches, "ms_per_launch": ms / launches,
-            "launches_per_eval": launches, "share_of_step": ms / total_prof_ms,
+            "launches_per_eval": launches,
+            # share of the timed step (the nyquist class runs on a side stream and overlaps, so the
+            # class times do not add up to the step)
+            "share_of_step": ms / ms_per_step,
             "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
             "note": "large chunks: the hybrid scratch (chunk x 4 MiB at 64^3) streams through HBM, "
                     "the plane kernel writes it and the pencil kernel reads it back (ncu DRAM bytes == "
