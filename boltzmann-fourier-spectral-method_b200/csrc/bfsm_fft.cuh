@@ -11,6 +11,10 @@
 // (one pad slot per 8 elements) and ROW chosen so that both the row-wise and the
 // column-wise passes are free of shared-memory bank conflicts for 16-byte accesses.
 //
+// The packed gain kernel (k_plane_gain3) uses a different plane scheme on the same radix
+// butterflies: three register stages (radix-R, 4x4 block, radix-R; N = 4R) over a plane with
+// row pitch N+1 and columns in natural order -- see bfsm_kernels.cuh.
+//
 // No cuFFT, no tensor cores: the whole path is fp64 SIMT (DFMA/DADD) + LDS/STS.
 #pragma once
 #include <cuda_runtime.h>
