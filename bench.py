@@ -340,6 +340,21 @@ def run_b200(args):
                 traffic = per_pair * pairs / launches
         except Exception:
             traffic = None
+        # second view: the FP64 pipe (the plane kernel is FP64/latency limited, not HBM limited).
+        # fp64 instructions per pair of the plane kernel from the committed ncu capture
+        # (profiles/r01_ncu_summary.json), peak measured live by a DFMA micro-benchmark.
+        fp64_view = None
+        try:
+            capi = B.submodule("_capi")
+            peak_dfma = capi.measure_fp64_peak(local_rank)
+            inst_per_pair = 12.8e6 * (N3 / 64 ** 3)   # ncu: 46.x fp64 instr per element and plane pass
+            rate = inst_per_pair * pairs / (prof["plane_gain"][0] * 1e-3)
+            fp64_view = {"peak_dfma_per_s_measured": peak_dfma, "peak_tflops_measured": 2 * peak_dfma / 1e12,
+                         "plane_kernel_fp64_inst_per_s": rate, "frac_of_issue_peak": rate / peak_dfma,
+                         "note": "fp64 instructions (DADD/DMUL/DFMA each count 1) issued per second by "
+                                 "the plane kernel over the measured DFMA issue rate"}
+        except Exception as exc:  # measurement aid only
+            fp64_view = {"error": str(exc)}
         roofline = {
             "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
@@ -362,6 +377,7 @@ def run_b200(args):
                 "achieved_gbs": (bytes_plane + bytes_pencil) * value / 1e9,
                 "frac": (bytes_plane + bytes_pencil) * value / 1e9 / peaks["hbm_gbs"],
                 "what": "algorithmic bytes of both gain kernels per evaluation x evals/s (whole step)"},
+            "fp64": fp64_view,
             "survey_contract": {
                 "bytes_per_eval": contract_bytes, "P_done": info["pairs_total"],
                 "folded": bool(info["folded"]),

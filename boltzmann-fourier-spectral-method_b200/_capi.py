@@ -17,7 +17,7 @@ EXPORTS = (
     "bfsm_version", "bfsm_last_error", "bfsm_plan_create", "bfsm_plan_destroy", "bfsm_collide",
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
     "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
-    "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host",
+    "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host", "bfsm_measure_fp64_peak",
 )
 
 KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final", "nyquist")
@@ -76,6 +76,8 @@ def load():
     lib.bfsm_collide_profiled.restype = ctypes.c_int
     lib.bfsm_collide_profiled.argtypes = [vp, vp, vp, vp, ctypes.POINTER(ctypes.c_double),
                                           ctypes.POINTER(ctypes.c_int)]
+    lib.bfsm_measure_fp64_peak.restype = ctypes.c_int
+    lib.bfsm_measure_fp64_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.bfsm_plan_set_chunk.restype = ctypes.c_int
     lib.bfsm_plan_set_chunk.argtypes = [vp, ctypes.c_int]
     _lib = lib
@@ -86,3 +88,10 @@ def check(rc):
     if rc != BFSM_OK:
         msg = load().bfsm_last_error()
         raise BfsmError(rc, msg.decode() if msg else "")
+
+
+def measure_fp64_peak(device=0):
+    """Peak DFMA/s of the FP64 pipe, measured on the device (bfsm_measure_fp64_peak)."""
+    out = ctypes.c_double()
+    check(load().bfsm_measure_fp64_peak(int(device), ctypes.byref(out)))
+    return out.value

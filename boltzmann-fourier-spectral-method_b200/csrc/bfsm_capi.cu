@@ -793,3 +793,55 @@ extern "C" int bfsm_copy_to_host(int device, void *dst_host, const void *src_dev
     CUDA_TRY(cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
     return BFSM_OK;
 }
+
+// ---- FP64 pipe peak (measurement aid): independent DFMA chains, no memory traffic ------------
+namespace {
+__global__ void __launch_bounds__(256) k_dfma_peak(double *out, int iters, double seed)
+{
+    double a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = seed + 1e-3 * (threadIdx.x + k);
+    const double m = 1.0000001, c = 1e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = fma(a[k], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 12345.6789) out[blockIdx.x * blockDim.x + threadIdx.x] = s; // keep the chains alive
+}
+} // namespace
+
+extern "C" int bfsm_measure_fp64_peak(int device, double *dfma_per_second)
+{
+    if (!dfma_per_second) return fail(BFSM_ERR_INVALID, "NULL argument");
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    CUDA_TRY(cudaMalloc((void **)&out, sizeof(double) * (size_t)blocks * threads));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, 0));
+        k_dfma_peak<<<blocks, threads>>>(out, iters, 1.0 + rep);
+        CUDA_TRY(cudaEventRecord(e1, 0));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        const double n = (double)blocks * threads * (double)iters * 64.0; // DFMA per launch
+        if (rep > 0) best = std::max(best, n / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *dfma_per_second = best;
+    return BFSM_OK;
+}

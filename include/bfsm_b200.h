@@ -144,6 +144,10 @@ enum {
 int bfsm_collide_profiled(bfsm_plan *plan, double *Q_dev, const double *f_dev, void *stream,
                           double *ms_by_class, int *launches_by_class);
 
+/* Measurement aid: peak rate of the FP64 pipe on `device` (independent DFMA chains, no memory
+ * traffic), in fused multiply-adds per second; 2x that is the usual FLOP/s figure. */
+int bfsm_measure_fp64_peak(int device, double *dfma_per_second);
+
 /* Tuning knob: pairs per launch of the gain kernels (0 = default heuristic). */
 int bfsm_plan_set_chunk(bfsm_plan *plan, int chunk_pairs);
 

@@ -260,3 +260,29 @@ def test_bkw_relaxation_error_vs_exact_solution():
     assert linf / np.abs(exact).max() < 5e-3   # measured 2.3e-3: set by the 32^3 discretisation of Q
     _, dv = inp.velocity_axis(Nv)
     assert abs(float(f.sum().item()) * dv ** 3 - 1.0) < 1e-5
+
+
+def test_argument_errors_are_python_exceptions():
+    Nv = 16
+    op, _, _ = make_operator(Nv, 2, 6)
+    f = torch.zeros(Nv ** 3, dtype=torch.float64, device="cuda")
+    with pytest.raises(TypeError):
+        op(torch.zeros(Nv ** 3, dtype=torch.float32, device="cuda"), f)      # wrong dtype
+    with pytest.raises(ValueError):
+        op(torch.zeros(10, dtype=torch.float64, device="cuda"), f)           # too small
+    with pytest.raises(TypeError):
+        op(torch.zeros(Nv ** 3, dtype=torch.float64), f)                     # Q on the host, f on the device
+    with pytest.raises(TypeError):
+        op(np.zeros(Nv ** 3, dtype=np.float32), np.zeros(Nv ** 3))           # host path, wrong dtype
+    op.close()
+    with pytest.raises(RuntimeError):
+        op(f.clone(), f)                                                     # closed plan
+    cold = B.BoltzmannOperatorB200(*quadrature(2, 6), Nv, Nv, Nv, 0.0, 1.0, 1.0)
+    with pytest.raises(RuntimeError):
+        cold(f.clone(), f)                                                   # initialize() not called
+    assert cold.getBackendName() == "B200"
+
+
+def test_fp64_peak_microbenchmark_is_plausible():
+    peak = B.submodule("_capi").measure_fp64_peak(0)
+    assert 5e12 < peak < 4e13      # B200: 148 SMs x 64 DFMA/clk x ~1.9 GHz ~ 1.8e13

@@ -143,3 +143,17 @@ def test_bkw_input_is_a_normalised_density():
     assert abs(f.sum() * dv ** 3 - 1.0) < 1e-6      # unit mass
     assert abs(Q.sum() * dv ** 3) < 1e-8            # collisions conserve mass
     assert f.min() >= 0
+
+
+def test_rk4_integrator_with_cpu_stand_in():
+    """The integrator is backend agnostic: with dQ/dt = -f it must reproduce exp(-t) to RK4 order."""
+    I = B.submodule("integrate")
+    f0 = np.array([1.0, 2.0, -3.0])
+    f, steps, evals = I.rk4_numpy(lambda x: -x, f0.copy(), 0.0, 1.0, 0.1)
+    assert steps == 10 and evals == 40
+    assert np.abs(f - f0 * np.exp(-1.0)).max() < 5e-6
+    # exact BKW solution: unit mass, positive for t > 6 ln(5/2)
+    fb = I.bkw_exact(32, 6.0)
+    _, dv = B.inputs.velocity_axis(32)
+    assert abs(fb.sum() * dv ** 3 - 1.0) < 1e-6 and fb.min() >= 0
+    assert np.array_equal(I.bkw_exact(16, 6.5), B.inputs.bkw(16)[0])
