@@ -135,7 +135,7 @@ int env_int(const char *name, int dflt)
 // ---- per-N launch geometry ------------------------------------------------------------
 template <int N> struct Launch;
 template <> struct Launch<64> { static constexpr int TG = 256, GROUPS = 2, MINB = 1, PG = 4, PMINB = 2, G = 1, CHUNK = 384, PSTAGES = 3; };
-template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, PMINB = 2, G = 4, CHUNK = 256, PSTAGES = 3; };
+template <> struct Launch<32> { static constexpr int TG = 128, GROUPS = 2, MINB = 2, PG = 8, PMINB = 2, G = 4, CHUNK = 1024, PSTAGES = 3; };
 template <> struct Launch<16> { static constexpr int TG = 64, GROUPS = 2, MINB = 4, PG = 8, PMINB = 2, G = 8, CHUNK = 1024, PSTAGES = 3; };
 
 template <int N> size_t plane_gain_smem()
@@ -565,7 +565,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bail(rc);
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
-    p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", N == 64 ? 4 : (N == 32 ? 24 : 64)));
+    p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", N == 64 ? 4 : (N == 32 ? 8 : 16)));
     p->async_pencil = env_int("BFSM_ASYNC_PENCIL", 1);
     p->plane3 = env_int("BFSM_PLANE3", 1);
     if ((rc = dev_alloc(p, (void **)&p->hyb,
