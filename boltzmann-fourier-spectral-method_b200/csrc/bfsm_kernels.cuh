@@ -278,37 +278,28 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 cplx v[R];
                 const cplx *frow = fpl + j * PITCH;
                 if (i < N) {
+                    // m_H = ((Re E + Im E) + (Re Et - Im Et))/2 with E = X*Z, X = ex[i] ey[j],
+                    // Z = ez[k], and Et = E(-l) = Xt*conj(Z) (Xt*Z at the Nyquist column k == H),
+                    // Xt = ex~[i] ey~[j] (conjugates except at the Nyquist index).  Expanding:
+                    //   m_H = A (Z.x+Z.y) + B (Z.x-Z.y),   A = (X.x+Xt.x)/2, B = (X.y-Xt.y)/2
+                    //   k == H:                            A = (X.x-Xt.y)/2, B = (X.y+Xt.x)/2
+                    // -- one divergence-free formula for interior and Nyquist rows alike.
                     const cplx exi = P[i], eyj = P[N + j];
-                    const cplx exy = cmul(exi, eyj);
-                    if (i != H && j != H) {
-                        // interior row: E(-l) = conj(E(l)) except at the z Nyquist column k == H
+                    const cplx X = cmul(exi, eyj);
+                    const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
+                    const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
+                    const cplx Xt = cmul(ext, eyt);
+                    const double cA = 0.5 * (X.x + Xt.x), cB = 0.5 * (X.y - Xt.y);
+                    const double nA = 0.5 * (X.x - Xt.y), nB = 0.5 * (X.y + Xt.x);
 #pragma unroll
-                        for (int a = 0; a < R; ++a) {
-                            const int k = 4 * a + b;
-                            const cplx ez = P[2 * N + k];
-                            const cplx e = cmul(exy, ez);
-                            double m = e.x + e.y;
-                            if (a == R / 2 && b == 0) { // k == H
-                                const cplx et = cmul(make_double2(exy.x, -exy.y), ez);
-                                m = 0.5 * ((e.x + e.y) + (et.x - et.y));
-                            }
-                            const cplx f = frow[k];
-                            v[a] = make_double2(m * f.x, m * f.y);
-                        }
-                    } else {
-                        const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
-                        const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
-                        const cplx exyt = cmul(ext, eyt);
-#pragma unroll
-                        for (int a = 0; a < R; ++a) {
-                            const int k = 4 * a + b;
-                            const cplx ez = P[2 * N + k];
-                            const cplx ezt = (k == H) ? ez : make_double2(ez.x, -ez.y);
-                            const cplx e = cmul(exy, ez), et = cmul(exyt, ezt);
-                            const double m = 0.5 * ((e.x + e.y) + (et.x - et.y));
-                            const cplx f = frow[k];
-                            v[a] = make_double2(m * f.x, m * f.y);
-                        }
+                    for (int a = 0; a < R; ++a) {
+                        const int k = 4 * a + b;
+                        const cplx ez = P[2 * N + k];
+                        const double zp = ez.x + ez.y, zm = ez.x - ez.y;
+                        const bool ny = (a == R / 2) && (b == 0); // k == H
+                        const double m = (ny ? nA : cA) * zp + (ny ? nB : cB) * zm;
+                        const cplx f = frow[k];
+                        v[a] = make_double2(m * f.x, m * f.y);
                     }
                 } else {
                     // Nyquist plane q = i - N: fixed axis q, free axes (axA rows, axB columns)
