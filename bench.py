@@ -375,9 +375,9 @@ def run_b200(args):
             "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
             "note": "large chunks: the hybrid scratch (chunk x 4 MiB at 64^3) streams through HBM, "
                     "the plane kernel writes it and the pencil kernel reads it back (ncu DRAM bytes == "
-                    "algorithmic bytes).  ncu on the plane kernel: FP64 pipe 49 %, l1tex data pipe 57 %, "
-                    "16 warps/SM (128 regs x 512 threads), top stalls barrier/short_scoreboard/"
-                    "math_pipe_throttle -> latency bound at register-limited occupancy; the pencil "
+                    "algorithmic bytes).  ncu on the plane kernel: FP64 pipe 52 %, l1tex data pipe 64 %, "
+                    "16 warps/SM (128 regs x 512 threads), top stalls mio_throttle/short_scoreboard/"
+                    "math_pipe_throttle -> smem instruction path + FP64 pipe co-limit at register-limited occupancy; the pencil "
                     "kernel reads at ~5.5 TB/s (HBM bound). See profiles/r01_ncu_summary.json",
             "pipeline_hbm": {
                 "bytes_per_eval": bytes_plane + bytes_pencil,
