@@ -44,11 +44,6 @@ double sincc(double x)
     return std::sin(x + eps) / (x + eps);
 }
 
-struct DeviceBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-};
-
 } // namespace
 
 struct bfsm_plan {
@@ -441,6 +436,11 @@ int lanes_prepare(bfsm_plan *p)
     lane_save(p, 0); // lane 0 == the plan's own scratch
     for (int k = 1; k < p->n_lanes; ++k) {
         int rc = lane_alloc(p, k);
+        if (rc == BFSM_ERR_NOMEM) { // not enough device memory for another lane: run with fewer
+            cudaGetLastError();
+            p->n_lanes = k;
+            break;
+        }
         if (rc) return rc;
     }
     return BFSM_OK;
@@ -451,30 +451,46 @@ int lane_alloc(bfsm_plan *p, int k)
     const size_t N3 = (size_t)N * N * N;
     bfsm_plan::Lane &L = p->lanes[k];
     if (L.allocated) return BFSM_OK;
+    L.allocated = true; // from here on lane_free() releases whatever was obtained
     auto need = [&](void **q, size_t bytes) -> int {
-        CUDA_TRY(cudaMalloc(q, bytes ? bytes : 16));
+        cudaError_t e = cudaMalloc(q, bytes ? bytes : 16);
+        if (e != cudaSuccess) {
+            *q = nullptr;
+            char b[200];
+            snprintf(b, sizeof b, "cudaMalloc(%zu bytes) for batch lane %d failed: %s", bytes, k,
+                     cudaGetErrorString(e));
+            return fail(e == cudaErrorMemoryAllocation ? BFSM_ERR_NOMEM : BFSM_ERR_CUDA, b);
+        }
         return BFSM_OK;
+    };
+    auto give_up = [&](int rc) {
+        std::string keep = g_err;
+        lane_free(p, k);
+        g_err = keep;
+        return rc;
     };
     int rc = BFSM_OK;
     const int nr = std::max(1, p->n_r_local);
-    if ((rc = need((void **)&L.fhat, sizeof(cplx) * N3))) return rc;
-    if ((rc = need((void **)&L.qhat, sizeof(cplx) * N3))) return rc;
-    if ((rc = need((void **)&L.tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local)))) return rc;
-    if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk))) return rc;
+    if ((rc = need((void **)&L.fhat, sizeof(cplx) * N3))) return give_up(rc);
+    if ((rc = need((void **)&L.qhat, sizeof(cplx) * N3))) return give_up(rc);
+    if ((rc = need((void **)&L.tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local)))) return give_up(rc);
+    if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
+        return give_up(rc);
     if ((rc = need((void **)&L.S, sizeof(double) * N3 * (size_t)(p->G + (p->packed ? p->GY : 0)) * nr)))
-        return rc;
+        return give_up(rc);
     if (p->packed) {
-        if ((rc = need((void **)&L.nyq, sizeof(cplx) * 3 * N * N))) return rc;
-        if ((rc = need((void **)&L.uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk))) return rc;
+        if ((rc = need((void **)&L.nyq, sizeof(cplx) * 3 * N * N))) return give_up(rc);
+        if ((rc = need((void **)&L.uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk))) return give_up(rc);
         if (p->use_side) {
-            CUDA_TRY(cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking));
+            if (cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) != cudaSuccess)
+                return give_up(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
             for (int j = 0; j < 2; ++j) {
-                CUDA_TRY(cudaEventCreateWithFlags(&L.ev_plane[j], cudaEventDisableTiming));
-                CUDA_TRY(cudaEventCreateWithFlags(&L.ev_nyq[j], cudaEventDisableTiming));
+                if (cudaEventCreateWithFlags(&L.ev_plane[j], cudaEventDisableTiming) != cudaSuccess ||
+                    cudaEventCreateWithFlags(&L.ev_nyq[j], cudaEventDisableTiming) != cudaSuccess)
+                    return give_up(fail(BFSM_ERR_CUDA, "cudaEventCreate failed"));
             }
         }
     }
-    L.allocated = true;
     return BFSM_OK;
 }
 
