@@ -354,7 +354,7 @@ def run_b200(args):
         try:
             capi = B.submodule("_capi")
             peak_dfma = capi.measure_fp64_peak(local_rank)
-            inst_per_pair = 12.8e6 * (N3 / 64 ** 3)   # ncu: 46.x fp64 instr per element and plane pass
+            inst_per_pair = 11.2e6 * (N3 / 64 ** 3)   # ncu (r01 v7 capture): DADD+DMUL+DFMA per pair at 64^3
             rate = inst_per_pair * pairs / (prof["plane_gain"][0] * 1e-3)
             fp64_view = {"peak_dfma_per_s_measured": peak_dfma, "peak_tflops_measured": 2 * peak_dfma / 1e12,
                          "plane_kernel_fp64_inst_per_s": rate, "frac_of_issue_peak": rate / peak_dfma,
