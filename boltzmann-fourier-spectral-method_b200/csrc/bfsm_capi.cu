@@ -54,7 +54,7 @@ struct bfsm_plan {
     int GY = 4;       // pair groups (= S partial slots) of k_nyq_accum
     int async_pencil = 1; // cp.async ring in the packed pencil kernel
     int plane3 = 1;       // 3-stage / 2-exchange plane kernel (packed mode)
-    int plane_ws = 0;     // warp-specialised pipelined plane kernel (packed mode, N = 64)
+    int plane_ws = 0;     // warp-specialised pipelined plane kernel (packed mode, N = 64): 1 or 2 S1 warpgroups
     int use_side = 1;     // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
     cudaStream_t side = nullptr;
     cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr};
@@ -172,7 +172,7 @@ template <int N> size_t plane_gain3_smem()
 
 template <int N> size_t plane_ws_smem()
 {
-    return sizeof(cplx) * ((size_t)3 * N * (N + 1) + (size_t)2 * 3 * N);
+    return sizeof(cplx) * ((size_t)3 * N * (N + 1) + (size_t)2 * 3 * N + (size_t)N);
 }
 
 template <int N> size_t pencil_async_smem()
@@ -189,9 +189,12 @@ template <int N> int configure_kernels()
     CUDA_TRY(cudaFuncSetAttribute(k_plane_gain3<N, Lc::GROUPS, Lc::MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain3_smem<N>()));
-    if constexpr (N == 64)
-        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if constexpr (N == 64) {
+        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)plane_ws_smem<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)plane_ws_smem<N>()));
+    }
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_async_smem<N>()));
@@ -289,10 +292,15 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
             if (N == 64 && p->packed && p->plane_ws) {
-                if constexpr (N == 64)
-                    k_plane_gain_ws<N><<<std::min(p->sm_count, (N + 3) * items), 384,
-                                         plane_ws_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                if constexpr (N == 64) {
+                    const int grid = std::min(p->sm_count, (N + 3) * items);
+                    if (p->plane_ws == 2)
+                        k_plane_gain_ws<N, 2><<<grid, 512, plane_ws_smem<N>(), st>>>(
+                            p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                    else
+                        k_plane_gain_ws<N, 1><<<grid, 384, plane_ws_smem<N>(), st>>>(
+                            p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                }
             } else if (p->packed && p->plane3)
                 k_plane_gain3<N, Lc::GROUPS, Lc::MINB>
                     <<<ctas, 4 * N * Lc::GROUPS, plane_gain3_smem<N>(), st>>>(
@@ -703,7 +711,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", N == 64 ? 4 : (N == 32 ? 8 : 16)));
     p->async_pencil = env_int("BFSM_ASYNC_PENCIL", 1);
     p->plane3 = env_int("BFSM_PLANE3", 1);
-    p->plane_ws = (N == 64) ? env_int("BFSM_PLANE_WS", 0) : 0;
+    p->plane_ws = (N == 64) ? env_int("BFSM_PLANE_WS", 2) : 0;
     p->n_lanes = std::min((int)bfsm_plan::MAX_LANES, std::max(1, env_int("BFSM_BATCH_LANES", 4)));
     if ((rc = dev_alloc(p, (void **)&p->hyb,
                         sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))

@@ -379,25 +379,29 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 
 // ---------------------------------------------------------------------------------------
 // k_plane_gain_ws (packed mode, N = 64): the three stages of k_plane_gain3 as a WARP-SPECIALISED
-// PIPELINE.  A CTA is three warpgroups of 128 threads, one per stage; every warpgroup walks the
-// CTA's whole item list and item n lives in plane buffer n % 3 on its way through the stages:
+// PIPELINE.  A CTA is NS1 + 2 warpgroups of 128 threads: NS1 for stage S1, one each for S2 and S3;
+// every warpgroup walks the CTA's whole item list and item n lives in plane buffer n % 3 on its
+// way through the stages:
 //
-//   S1 warpgroup (240 registers): keeps its 2 x 16 entries of the fhat plane IN REGISTERS for as long
-//       as the plane does not change (no shared-memory copy of fhat, no per-item re-read), applies
-//       the real multiplier m_H, radix-16 along z, stores rows            -> full1[buf]
-//   S2 warpgroup (152 registers): 4 x 4 block in place (both twiddles)     -> full2[buf]
-//   S3 warpgroup (104 registers): radix-16 along y, natural-order global store -> empty[buf]
+//   S1 warpgroup(s): keep their entries of the fhat plane IN REGISTERS for as long as the plane does
+//       not change (no per-item re-read of fhat from shared memory), apply the real multiplier m_H,
+//       radix-16 along z, store rows                                       -> full1[buf]
+//   S2 warpgroup: 4 x 4 blocks in place (both twiddles)                    -> full2[buf]
+//   S3 warpgroup: radix-16 along y, natural-order global store             -> empty[buf]
 //
 // Why: in k_plane_gain3 all warps of a group are in the same stage, so the SM alternates between
 // LDS/STS bursts and FP64 butterflies (ncu: l1tex data pipe 64 %, FP64 pipe 52 %, both idle a third
-// of the time); here every SM sub-partition holds one warp of each stage, so that the LSU and the
+// of the time); here every SM sub-partition holds a warp of each stage, so that the LSU and the
 // FP64 pipe always have a customer, and the fhat re-read (one of six 16-byte accesses per element)
-// is gone.  Hand-offs are named barriers used as producer/consumer pairs (bar.arrive by the 128
-// producers, bar.sync by the 128 consumers, count 256): ids 1-3 full1, 4-6 full2, 7-9 empty, 10 is
-// the S1 warpgroup's own barrier (phase-table staging).  S3 releases a buffer only after the global
-// stores that depend on its loads, so the buffer cannot be overwritten under an outstanding LDS.
-// Registers move between the warpgroups with setmaxnreg (launch: 384 threads x 168).
-// The arithmetic is instruction-for-instruction that of k_plane_gain3: results are bitwise equal.
+// is gone.  Hand-offs are named barriers used as producer/consumer pairs (bar.arrive by the
+// producers, bar.sync by the consumers): ids 1-3 full1, 4-6 full2, 7-9 empty, 10 is the S1
+// warpgroups' own barrier (phase-table and plane staging).  S3 releases a buffer only after the
+// global stores that depend on its loads, so a buffer cannot be overwritten under an outstanding
+// LDS.  Registers move between the warpgroups with setmaxnreg:
+//   NS1 = 1: 384 threads launched at 168 -> S1 240 | S2 152 | S3 112      (2 units per S1 thread)
+//   NS1 = 2: 512 threads launched at 128 -> S1 2 x 152 | S2 104 | S3 104  (1 unit per S1 thread)
+// The arithmetic is that of k_plane_gain3 (same formulas, same operation order; the results agree
+// to the last bit or two -- the compiler contracts a few multiply-adds differently).
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void bar_sync_n(int id, int n)
 {
@@ -407,23 +411,37 @@ __device__ __forceinline__ void bar_arrive_n(int id, int n)
 {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
+template <int REGS> __device__ __forceinline__ void reg_alloc()
+{
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS));
+}
+template <int REGS> __device__ __forceinline__ void reg_dealloc()
+{
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
+}
 
-template <int N>
-__global__ void __launch_bounds__(384, 1)
+template <int N, int NS1>
+__global__ void __launch_bounds__((NS1 + 2) * 128, 1)
 k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items,
                 const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
                 cplx *__restrict__ uvw)
 {
-    constexpr int R = N / 4, GT = 128, U = (4 * N) / GT, PITCH = N + 1, H = N / 2, NPL = N + 3;
-    constexpr int NBUF = 3;
+    constexpr int R = N / 4, GT = 128, PITCH = N + 1, H = N / 2, NPL = N + 3, NBUF = 3;
+    constexpr int T1 = NS1 * GT;          // threads of stage S1
+    constexpr int U1 = (4 * N) / T1;      // S1 units (row, residue) per thread and item
+    constexpr int U = (4 * N) / GT;       // S2 / S3 units per thread and item
     constexpr int BAR_FULL1 = 1, BAR_FULL2 = 4, BAR_EMPTY = 7, BAR_S1 = 10;
-    static_assert(N == 64 && U == 2 && R == 16, "k_plane_gain_ws is written for N = 64");
+    constexpr int REG_S1 = NS1 == 1 ? 240 : 152, REG_S2 = NS1 == 1 ? 152 : 104,
+                  REG_S3 = NS1 == 1 ? 112 : 104;
+    static_assert(N == 64 && R == 16 && U == 2 && (NS1 == 1 || NS1 == 2),
+                  "k_plane_gain_ws is written for N = 64");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *bufs = reinterpret_cast<cplx *>(smem_raw);          // NBUF x (N x PITCH)
     cplx *phs = bufs + NBUF * N * PITCH;                      // 2 x 3N (S1's phase tables)
+    cplx *tws = phs + 2 * 3 * N;                              // N twiddles exp(+2 pi i t/N)
 
-    const int wg = threadIdx.x / GT, t = threadIdx.x % GT;
+    const int wg = threadIdx.x / GT;
 
     // this CTA's share of the flat work list, index = plane * n_items + item
     const long long total = (long long)NPL * n_items;
@@ -431,57 +449,65 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
     const int cnt = w_hi - w_lo;
 
-    if (wg == 0) {
+    if (threadIdx.x < N) tws[threadIdx.x] = __ldg(&twtab[threadIdx.x]);
+    __syncthreads();
+
+    if (wg < NS1) {
         // =========================== S1: phase-weighted fhat, radix-R along z ===================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
-        const int b = t / 32, jl = t % 32; // residue (warp uniform), rows jl and jl + 32
-        cplx fr[U][R];                     // fr[u][a] = plane[jl + 32u][4a + b]
+        reg_alloc<REG_S1>();
+        const int ts = threadIdx.x;            // 0 .. T1-1
+        const int j = ts % N, b0 = ts / N;     // unit u: row j, residue b0 + (T1/N) u
+        cplx fr[U1][R];                        // fr[u][a] = plane[j][4a + b_u]
         int cur_plane = -1;
-        cplx nxt[2];
-        if (cnt > 0) { // phase table of the first item -> slot 0
-            const int i0 = w_lo / n_items, it0 = w_lo - i0 * n_items;
-            const cplx *src = phase + (size_t)(pair0 + it0) * 3 * N;
-            phs[t] = __ldg(&src[t]);
-            if (t + GT < 3 * N) phs[t + GT] = __ldg(&src[t + GT]);
-        }
-        bar_sync_n(BAR_S1, GT);
+        // the phase table of item n+1 is copied (cp.async) into the other slot while item n is computed
+        auto stage_phase = [&](int it_src, int slot_dst) {
+            const cplx *src = phase + (size_t)(pair0 + it_src) * 3 * N;
+            cplx *dstp = phs + slot_dst * 3 * N;
+            if (ts < 3 * N) cp_async16(dstp + ts, src + ts);
+            if (NS1 == 1 && ts + GT < 3 * N) cp_async16(dstp + ts + GT, src + ts + GT);
+        };
+        int i = w_lo / n_items, it = w_lo - i * n_items; // plane and item of the current list entry
+        if (cnt > 0) stage_phase(it, 0);
+        cp_async_commit();
+        cp_async_wait<0>();
+        bar_sync_n(BAR_S1, T1);
         int buf_id = 0, slot = 0;
         for (int n = 0; n < cnt; ++n) {
-            const int w = w_lo + n;
-            const int i = w / n_items, it = w - i * n_items;
-            if (i != cur_plane) { // (re)load this thread's entries of the plane
+            // next entry of the flat list: next pair, or pair 0 of the next plane
+            const int itn = (it + 1 == n_items) ? 0 : it + 1;
+            if (n + 1 < cnt) stage_phase(itn, slot ^ 1);
+            cp_async_commit();
+            cplx *buf = bufs + buf_id * N * PITCH;
+            if (n >= NBUF) bar_sync_n(BAR_EMPTY + buf_id, T1 + GT); // S3 is done with item n - NBUF
+            if (i != cur_plane) {
+                // new plane: coalesced copy into the (free) pipeline buffer, then every thread picks
+                // its entries -- the strided direct load costs ~10 us per plane change
                 const cplx *srcp = (i < N) ? fhat + (size_t)i * N * N : nyq + (size_t)(i - N) * N * N;
+#pragma unroll 8
+                for (int e = ts; e < N * N; e += T1) buf[(e / N) * PITCH + (e % N)] = __ldg(&srcp[e]);
+                bar_sync_n(BAR_S1, T1);
 #pragma unroll
-                for (int u = 0; u < U; ++u)
+                for (int u = 0; u < U1; ++u)
 #pragma unroll
-                    for (int a = 0; a < R; ++a) fr[u][a] = __ldg(&srcp[(jl + 32 * u) * N + 4 * a + b]);
+                    for (int a = 0; a < R; ++a) fr[u][a] = buf[j * PITCH + 4 * a + b0 + (T1 / N) * u];
+                bar_sync_n(BAR_S1, T1); // all entries are in registers before anybody overwrites buf
                 cur_plane = i;
             }
-            const bool have_next = n + 1 < cnt;
-            if (have_next) { // next item of the flat list: next pair, or pair 0 of the next plane
-                const int itn = (it + 1 == n_items) ? 0 : it + 1;
-                const cplx *src = phase + (size_t)(pair0 + itn) * 3 * N;
-                nxt[0] = __ldg(&src[t]);
-                if (t + GT < 3 * N) nxt[1] = __ldg(&src[t + GT]);
-            }
             const cplx *P = phs + slot * 3 * N;
-            cplx *buf = bufs + buf_id * N * PITCH;
-            if (n >= NBUF) bar_sync_n(BAR_EMPTY + buf_id, 2 * GT); // S3 is done with item n - NBUF
 
             if (i < N) {
-                const cplx exi = P[i];
+                // m_H = A (Z.x+Z.y) + B (Z.x-Z.y), see k_plane_gain3
+                const cplx exi = P[i], eyj = P[N + j];
+                const cplx X = cmul(exi, eyj);
                 const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
+                const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
+                const cplx Xt = cmul(ext, eyt);
+                const double cA = 0.5 * (X.x + Xt.x), cB = 0.5 * (X.y - Xt.y);
+                const double nA = 0.5 * (X.x - Xt.y), nB = 0.5 * (X.y + Xt.x);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = jl + 32 * u;
+                for (int u = 0; u < U1; ++u) {
+                    const int b = b0 + (T1 / N) * u;
                     cplx v[R];
-                    // m_H = A (Z.x+Z.y) + B (Z.x-Z.y), see k_plane_gain3
-                    const cplx eyj = P[N + j];
-                    const cplx X = cmul(exi, eyj);
-                    const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
-                    const cplx Xt = cmul(ext, eyt);
-                    const double cA = 0.5 * (X.x + Xt.x), cB = 0.5 * (X.y - Xt.y);
-                    const double nA = 0.5 * (X.x - Xt.y), nB = 0.5 * (X.y + Xt.x);
 #pragma unroll
                     for (int a = 0; a < R; ++a) {
                         const int k = 4 * a + b;
@@ -503,14 +529,14 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 const int axA = (nq == 0) ? 1 : 0, axB = (nq == 2) ? 1 : 2;
                 const cplx efix = P[nq * N + H];
                 const double sw = 0.5 * sqrt(__ldg(&pair_w[pair0 + it]));
+                const cplx ea = P[axA * N + j];
+                const cplx eat = (j == H) ? ea : make_double2(ea.x, -ea.y);
+                const cplx fa = cmul(efix, ea), fat = cmul(efix, eat);
+                const bool zero_row = (nq >= 1) && (j == H);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = jl + 32 * u;
+                for (int u = 0; u < U1; ++u) {
+                    const int b = b0 + (T1 / N) * u;
                     cplx v[R];
-                    const cplx ea = P[axA * N + j];
-                    const cplx eat = (j == H) ? ea : make_double2(ea.x, -ea.y);
-                    const cplx fa = cmul(efix, ea), fat = cmul(efix, eat);
-                    const bool zero_row = (nq >= 1) && (j == H);
 #pragma unroll
                     for (int a = 0; a < R; ++a) {
                         const int k = 4 * a + b;
@@ -528,35 +554,30 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                     for (int k1 = 0; k1 < R; ++k1) row[k1] = v[dft_reg<R>(k1)];
                 }
             }
-            bar_arrive_n(BAR_FULL1 + buf_id, 2 * GT);
-            if (have_next) {
-                cplx *dstp = phs + (slot ^ 1) * 3 * N;
-                dstp[t] = nxt[0];
-                if (t + GT < 3 * N) dstp[t + GT] = nxt[1];
-            }
-            bar_sync_n(BAR_S1, GT); // next table visible; everyone is done reading the current one
+            bar_arrive_n(BAR_FULL1 + buf_id, T1 + GT);
+            cp_async_wait<0>();
+            bar_sync_n(BAR_S1, T1); // next table visible; everyone is done reading the current one
             slot ^= 1;
             buf_id = (buf_id + 1 == NBUF) ? 0 : buf_id + 1;
+            if (itn == 0) ++i;
+            it = itn;
         }
         // absorb S3's releases of the last items so that every barrier ends balanced
-        for (int n = (cnt > NBUF ? cnt - NBUF : 0); n < cnt; ++n) bar_sync_n(BAR_EMPTY + n % NBUF, 2 * GT);
-    } else if (wg == 1) {
+        for (int n = (cnt > NBUF ? cnt - NBUF : 0); n < cnt; ++n)
+            bar_sync_n(BAR_EMPTY + n % NBUF, T1 + GT);
+    } else if (wg == NS1) {
         // =========================== S2: 4 x 4 blocks in place ===================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 152;");
+        reg_dealloc<REG_S2>();
+        const int t = threadIdx.x - NS1 * GT;
         // unit q = t + 128 u: b' = q % R = t % R, k1 = q / R = t / R + 8 u
         const int s2b = t % R;
-        cplx wz[U][3], wy[3];
+        cplx wy[3];
 #pragma unroll
-        for (int m = 1; m < 4; ++m) {
-            wy[m - 1] = __ldg(&twtab[(m * s2b) & (N - 1)]);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-                wz[u][m - 1] = __ldg(&twtab[(m * (t / R + (GT / R) * u)) & (N - 1)]);
-        }
+        for (int m = 1; m < 4; ++m) wy[m - 1] = tws[(m * s2b) & (N - 1)];
         int buf_id = 0;
         for (int n = 0; n < cnt; ++n) {
             cplx *buf = bufs + buf_id * N * PITCH;
-            bar_sync_n(BAR_FULL1 + buf_id, 2 * GT);
+            bar_sync_n(BAR_FULL1 + buf_id, T1 + GT);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int s2k = t / R + (GT / R) * u;
@@ -566,10 +587,13 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 for (int ap = 0; ap < 4; ++ap)
 #pragma unroll
                     for (int bb = 0; bb < 4; ++bb) e[ap][bb] = blk[(R * ap) * PITCH + R * bb];
+                cplx wz[3];
+#pragma unroll
+                for (int m = 1; m < 4; ++m) wz[m - 1] = tws[(m * s2k) & (N - 1)];
 #pragma unroll
                 for (int ap = 0; ap < 4; ++ap) {
 #pragma unroll
-                    for (int bb = 1; bb < 4; ++bb) e[ap][bb] = cmul(e[ap][bb], wz[u][bb - 1]);
+                    for (int bb = 1; bb < 4; ++bb) e[ap][bb] = cmul(e[ap][bb], wz[bb - 1]);
                     dft4<+1>(e[ap][0], e[ap][1], e[ap][2], e[ap][3]);
                 }
 #pragma unroll
@@ -588,16 +612,17 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         }
     } else {
         // =========================== S3: radix-R along y, natural-order store ====================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        reg_dealloc<REG_S3>();
+        const int t = threadIdx.x - (NS1 + 1) * GT;
         // unit q = t + 128 u: column slot q % N = t % N, k1' = q / N = t / N + 2 u
         const int s3slot = t % N;
         int buf_id = 0;
+        int i = w_lo / n_items, it = w_lo - i * n_items;
         for (int n = 0; n < cnt; ++n) {
-            const int w = w_lo + n;
-            const int i = w / n_items, it = w - i * n_items;
             const cplx *buf = bufs + buf_id * N * PITCH;
             cplx *dst = (i < N) ? hyb + ((size_t)it * N + i) * N * N
                                 : uvw + ((size_t)it * 3 + (i - N)) * N * N;
+            if (++it == n_items) { it = 0; ++i; }
             bar_sync_n(BAR_FULL2 + buf_id, 2 * GT);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -610,7 +635,7 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 #pragma unroll
                 for (int k2 = 0; k2 < R; ++k2) dst[(s3k + 4 * k2) * N + s3slot] = v[dft_reg<R>(k2)];
             }
-            bar_arrive_n(BAR_EMPTY + buf_id, 2 * GT); // after the stores that consumed the loads
+            bar_arrive_n(BAR_EMPTY + buf_id, T1 + GT); // after the stores that consumed the loads
             buf_id = (buf_id + 1 == NBUF) ? 0 : buf_id + 1;
         }
     }
