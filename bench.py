@@ -332,36 +332,45 @@ def run_b200(args):
         ms, launches = prof[cls]
         bytes_cls = bytes_plane if cls == "plane_gain" else bytes_pencil
         achieved = bytes_cls / (ms * 1e-3) / 1e9
-        kernel_name = {("plane_gain", 1): "k_plane_gain3", ("plane_gain", 0): "k_plane_gain",
-                       ("pencil_gain", 1): "k_pencil_gain_async", ("pencil_gain", 0): "k_pencil_gain"}[
-                           (cls, int(bool(info["packed"])))]
+        plane_names = {0: "k_plane_gain", 1: "k_plane_gain3", 2: "k_plane_gain_ws"}
+        if cls == "plane_gain":
+            kernel_name = plane_names[info["plane_kernel"]]
+        else:
+            kernel_name = "k_pencil_gain_async" if info["packed"] else "k_pencil_gain"
+        plane_name = plane_names[info["plane_kernel"]]
         contract_bytes = 96 * N3 * info["pairs_total"] + 128 * N3
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture
-        # (profiles/r01_ncu_summary.json), per launch, scaled to this run's pairs per launch
-        traffic = None
+        # ncu figures of the gain kernels from the committed `ncu --set full` captures
+        # (profiles/r01_ncu_summary.json): DRAM bytes per launch (scaled to this run's pairs per
+        # launch) and fp64 instructions per pair
+        summary = {}
         try:
             with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as fh:
-                cap = json.load(fh)["full_capture_k_plane_gain3"]
-            if cls == "plane_gain" and info["packed"] and Nv == 64:
-                per_pair = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["pairs_in_launch"]
-                traffic = per_pair * pairs / launches
+                summary = json.load(fh)
         except Exception:
-            traffic = None
-        # second view: the FP64 pipe (the plane kernel is FP64/latency limited, not HBM limited).
-        # fp64 instructions per pair of the plane kernel from the committed ncu capture
-        # (profiles/r01_ncu_summary.json), peak measured live by a DFMA micro-benchmark.
+            summary = {}
+        cap = summary.get("full_capture_" + kernel_name) if Nv == 64 else None
+        traffic = None
+        if cap and "dram_bytes_read" in cap:
+            per_pair = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["pairs_in_launch"]
+            traffic = per_pair * pairs / launches
+        # second view: the FP64 pipe (the plane kernel is LSU/FP64 limited, not HBM limited).
+        # fp64 instructions per pair of the plane kernel from the committed ncu capture, peak
+        # measured live by a DFMA micro-benchmark.
         fp64_view = None
         try:
             capi = B.submodule("_capi")
             peak_dfma = capi.measure_fp64_peak(local_rank)
-            inst_per_pair = 11.2e6 * (N3 / 64 ** 3)   # ncu (r01 v7 capture): DADD+DMUL+DFMA per pair at 64^3
+            plane_cap = summary.get("full_capture_" + plane_name, {})
+            inst_per_pair = plane_cap.get("fp64_inst_per_pair", 11.2e6) * (N3 / 64 ** 3)
             rate = inst_per_pair * pairs / (prof["plane_gain"][0] * 1e-3)
             fp64_view = {"peak_dfma_per_s_measured": peak_dfma, "peak_tflops_measured": 2 * peak_dfma / 1e12,
-                         "plane_kernel_fp64_inst_per_s": rate, "frac_of_issue_peak": rate / peak_dfma,
+                         "plane_kernel": plane_name, "plane_kernel_fp64_inst_per_s": rate,
+                         "frac_of_issue_peak": rate / peak_dfma,
                          "note": "fp64 instructions (DADD/DMUL/DFMA each count 1) issued per second by "
                                  "the plane kernel over the measured DFMA issue rate"}
         except Exception as exc:  # measurement aid only
             fp64_view = {"error": str(exc)}
+        note = summary.get("roofline_note", "see profiles/r01_ncu_summary.json")
         roofline = {
             "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"],
             "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
@@ -373,12 +382,7 @@ def run_b200(args):
             # class times do not add up to the step)
             "share_of_step": ms / ms_per_step,
             "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
-            "note": "large chunks: the hybrid scratch (chunk x 4 MiB at 64^3) streams through HBM, "
-                    "the plane kernel writes it and the pencil kernel reads it back (ncu DRAM bytes == "
-                    "algorithmic bytes).  ncu on the plane kernel: FP64 pipe 52 %, l1tex data pipe 64 %, "
-                    "16 warps/SM (128 regs x 512 threads), top stalls mio_throttle/short_scoreboard/"
-                    "math_pipe_throttle -> smem instruction path + FP64 pipe co-limit at register-limited occupancy; the pencil "
-                    "kernel reads at ~5.5 TB/s (HBM bound). See profiles/r01_ncu_summary.json",
+            "note": note,
             "pipeline_hbm": {
                 "bytes_per_eval": bytes_plane + bytes_pencil,
                 "achieved_gbs": (bytes_plane + bytes_pencil) * value / 1e9,

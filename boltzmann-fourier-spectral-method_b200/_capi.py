@@ -28,7 +28,7 @@ class PlanInfo(ctypes.Structure):
         ("n", ctypes.c_int), ("n_r", ctypes.c_int), ("n_s", ctypes.c_int),
         ("folded", ctypes.c_int), ("packed", ctypes.c_int), ("pairs_total", ctypes.c_int), ("pairs_local", ctypes.c_int),
         ("chunk_pairs", ctypes.c_int), ("launches_per_cell", ctypes.c_int),
-        ("scratch_bytes", ctypes.c_longlong),
+        ("scratch_bytes", ctypes.c_longlong), ("plane_kernel", ctypes.c_int),
     ]
 
 

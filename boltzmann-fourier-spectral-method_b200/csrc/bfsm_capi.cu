@@ -711,7 +711,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", N == 64 ? 4 : (N == 32 ? 8 : 16)));
     p->async_pencil = env_int("BFSM_ASYNC_PENCIL", 1);
     p->plane3 = env_int("BFSM_PLANE3", 1);
-    p->plane_ws = (N == 64) ? env_int("BFSM_PLANE_WS", 2) : 0;
+    p->plane_ws = (N == 64) ? env_int("BFSM_PLANE_WS", 1) : 0;
     p->n_lanes = std::min((int)bfsm_plan::MAX_LANES, std::max(1, env_int("BFSM_BATCH_LANES", 4)));
     if ((rc = dev_alloc(p, (void **)&p->hyb,
                         sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
@@ -812,6 +812,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->chunk_pairs = p->chunk;
     info->launches_per_cell = do_launch_count(p);
     info->scratch_bytes = p->scratch_bytes;
+    info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : (p->plane3 ? 1 : 0);
     return BFSM_OK;
 }
 

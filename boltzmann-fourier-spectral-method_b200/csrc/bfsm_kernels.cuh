@@ -243,9 +243,15 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         wy[m - 1] = __ldg(&twtab[(m * s2b) & (N - 1)]);
     }
 
-    const long long total = (long long)NPL * n_items;
-    const int w_lo = (int)((total * blockIdx.x) / gridDim.x);
-    const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
+    // Work split: the flat list index = plane * n_items + item has two classes of entries, the N
+    // regular planes and the 3 (costlier) Nyquist planes; every CTA takes an equal share of EACH
+    // class, so that all CTAs finish together (with one contiguous range per CTA the owners of the
+    // Nyquist planes ran 10 % longer than the rest -- ncu sm__cycles_active max vs avg).
+    for (int part = 0; part < 2; ++part) {
+    const long long total = (long long)(part == 0 ? N : NPL - N) * n_items;
+    const int base = part == 0 ? 0 : N * n_items;
+    const int w_lo = base + (int)((total * blockIdx.x) / gridDim.x);
+    const int w_hi = base + (int)((total * (blockIdx.x + 1)) / gridDim.x);
 
     int w = w_lo;
     while (w < w_hi) {
@@ -375,6 +381,7 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         }
         w = i * n_items + it_hi;
     }
+    } // part
 }
 
 // ---------------------------------------------------------------------------------------
@@ -420,6 +427,17 @@ template <int REGS> __device__ __forceinline__ void reg_dealloc()
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS));
 }
 
+// Walks a CTA's entries of the flat (plane, item) list: `leftA` entries of a first contiguous range,
+// then a second range starting at (iB, itB).
+struct ItemWalk {
+    int i, it, n_items, leftA, iB, itB;
+    __device__ __forceinline__ void next()
+    {
+        if (--leftA == 0) { i = iB; it = itB; }
+        else if (++it == n_items) { it = 0; ++i; }
+    }
+};
+
 template <int N, int NS1>
 __global__ void __launch_bounds__((NS1 + 2) * 128, 1)
 k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
@@ -443,11 +461,18 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 
     const int wg = threadIdx.x / GT;
 
-    // this CTA's share of the flat work list, index = plane * n_items + item
-    const long long total = (long long)NPL * n_items;
-    const int w_lo = (int)((total * blockIdx.x) / gridDim.x);
-    const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
-    const int cnt = w_hi - w_lo;
+    // this CTA's share of the flat work list (index = plane * n_items + item): an equal share of the
+    // N regular planes, then an equal share of the 3 costlier Nyquist planes (see k_plane_gain3)
+    const long long totA = (long long)N * n_items, totB = (long long)(NPL - N) * n_items;
+    const int a_lo = (int)((totA * blockIdx.x) / gridDim.x), a_hi = (int)((totA * (blockIdx.x + 1)) / gridDim.x);
+    const int b_lo = (int)((totB * blockIdx.x) / gridDim.x), b_hi = (int)((totB * (blockIdx.x + 1)) / gridDim.x);
+    const int cntA = a_hi - a_lo, cnt = cntA + (b_hi - b_lo);
+    ItemWalk walk0;
+    walk0.n_items = n_items;
+    walk0.iB = N + b_lo / n_items;
+    walk0.itB = b_lo % n_items;
+    if (cntA > 0) { walk0.i = a_lo / n_items; walk0.it = a_lo % n_items; walk0.leftA = cntA; }
+    else          { walk0.i = walk0.iB;       walk0.it = walk0.itB;      walk0.leftA = -1; }
 
     if (threadIdx.x < N) tws[threadIdx.x] = __ldg(&twtab[threadIdx.x]);
     __syncthreads();
@@ -466,16 +491,16 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             if (ts < 3 * N) cp_async16(dstp + ts, src + ts);
             if (NS1 == 1 && ts + GT < 3 * N) cp_async16(dstp + ts + GT, src + ts + GT);
         };
-        int i = w_lo / n_items, it = w_lo - i * n_items; // plane and item of the current list entry
-        if (cnt > 0) stage_phase(it, 0);
+        ItemWalk wk = walk0;                   // plane and item of the current list entry
+        if (cnt > 0) stage_phase(wk.it, 0);
         cp_async_commit();
         cp_async_wait<0>();
         bar_sync_n(BAR_S1, T1);
         int buf_id = 0, slot = 0;
         for (int n = 0; n < cnt; ++n) {
-            // next entry of the flat list: next pair, or pair 0 of the next plane
-            const int itn = (it + 1 == n_items) ? 0 : it + 1;
-            if (n + 1 < cnt) stage_phase(itn, slot ^ 1);
+            const int i = wk.i, it = wk.it;
+            wk.next();                         // next entry: its phase table goes to the other slot
+            if (n + 1 < cnt) stage_phase(wk.it, slot ^ 1);
             cp_async_commit();
             cplx *buf = bufs + buf_id * N * PITCH;
             if (n >= NBUF) bar_sync_n(BAR_EMPTY + buf_id, T1 + GT); // S3 is done with item n - NBUF
@@ -559,8 +584,6 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             bar_sync_n(BAR_S1, T1); // next table visible; everyone is done reading the current one
             slot ^= 1;
             buf_id = (buf_id + 1 == NBUF) ? 0 : buf_id + 1;
-            if (itn == 0) ++i;
-            it = itn;
         }
         // absorb S3's releases of the last items so that every barrier ends balanced
         for (int n = (cnt > NBUF ? cnt - NBUF : 0); n < cnt; ++n)
@@ -617,12 +640,12 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         // unit q = t + 128 u: column slot q % N = t % N, k1' = q / N = t / N + 2 u
         const int s3slot = t % N;
         int buf_id = 0;
-        int i = w_lo / n_items, it = w_lo - i * n_items;
+        ItemWalk wk = walk0;
         for (int n = 0; n < cnt; ++n) {
             const cplx *buf = bufs + buf_id * N * PITCH;
-            cplx *dst = (i < N) ? hyb + ((size_t)it * N + i) * N * N
-                                : uvw + ((size_t)it * 3 + (i - N)) * N * N;
-            if (++it == n_items) { it = 0; ++i; }
+            cplx *dst = (wk.i < N) ? hyb + ((size_t)wk.it * N + wk.i) * N * N
+                                   : uvw + ((size_t)wk.it * 3 + (wk.i - N)) * N * N;
+            wk.next();
             bar_sync_n(BAR_FULL2 + buf_id, 2 * GT);
 #pragma unroll
             for (int u = 0; u < U; ++u) {

@@ -122,6 +122,8 @@ typedef struct {
     int chunk_pairs;         /* pairs per gain-kernel launch */
     int launches_per_cell;   /* kernel launches issued per evaluated cell */
     long long scratch_bytes; /* device memory owned by the plan */
+    int plane_kernel;        /* gain plane kernel in use: 0 k_plane_gain (4-pass), 1 k_plane_gain3,
+                                2 k_plane_gain_ws (warp-specialised pipeline, 64^3 packed mode) */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);
@@ -134,7 +136,7 @@ int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);
  */
 enum {
     BFSM_KCLASS_FORWARD = 0,     /* k_plane<REAL> + k_pencil_fwd : fhat = FFT3(f)          */
-    BFSM_KCLASS_PLANE_GAIN = 1,  /* k_plane_gain  : phase multiply + 2-D inverse FFT (y,z)  */
+    BFSM_KCLASS_PLANE_GAIN = 1,  /* k_plane_gain* : phase multiply + 2-D inverse FFT (y,z)  */
     BFSM_KCLASS_PENCIL_GAIN = 2, /* k_pencil_gain : inverse FFT (x) + product + accumulate  */
     BFSM_KCLASS_ACCUM = 3,       /* k_plane<REAL> + k_pencil_accum : Qhat = sum_r ...       */
     BFSM_KCLASS_FINAL = 4,       /* k_plane<FINAL> + k_pencil_final : loss + combine        */
