@@ -71,6 +71,7 @@ struct bfsm_plan {
     // device tables
     cplx *tw = nullptr;       // [N] exp(+2 pi i t/N)
     cplx *phase = nullptr;    // [pairs_local][3][N]
+    cplx *zpm = nullptr;      // [pairs_local][N]  (Re+Im, Re-Im) of the z phase (k_plane_gain_ws)
     int *pair_r = nullptr;    // [pairs_local] local radius index
     double *pair_w = nullptr; // [pairs_local] spherical weight (x2 when folded)
     int *r_end = nullptr;     // [n_r_local] one past the last local pair of that radius
@@ -172,7 +173,7 @@ template <int N> size_t plane_gain3_smem()
 
 template <int N> size_t plane_ws_smem()
 {
-    return sizeof(cplx) * ((size_t)3 * N * (N + 1) + (size_t)2 * 3 * N + (size_t)N);
+    return sizeof(cplx) * ((size_t)3 * N * (N + 1) + (size_t)2 * 4 * N + (size_t)N);
 }
 
 template <int N> size_t pencil_async_smem()
@@ -296,10 +297,10 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                     const int grid = std::min(p->sm_count, (N + 3) * items);
                     if (p->plane_ws == 2)
                         k_plane_gain_ws<N, 2><<<grid, 512, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
                     else
                         k_plane_gain_ws<N, 1><<<grid, 384, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
                 }
             } else if (p->packed && p->plane3)
                 k_plane_gain3<N, Lc::GROUPS, Lc::MINB>
@@ -699,6 +700,17 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     };
     if ((rc = upload(p, &p->tw, h_tw))) return bail(rc);
     if ((rc = upload(p, &p->phase, h_phase))) return bail(rc);
+    {
+        // the packed multiplier only needs Re+Im and Re-Im of the z phase: tabulated once here
+        // (the same two IEEE additions the kernels would do per element and pair)
+        std::vector<cplx> h_zpm((size_t)std::max(p->pairs_local, 1) * N);
+        for (int q = 0; q < p->pairs_local; ++q)
+            for (int t = 0; t < N; ++t) {
+                const cplx ez = h_phase[((size_t)q * 3 + 2) * N + t];
+                h_zpm[(size_t)q * N + t] = make_double2(ez.x + ez.y, ez.x - ez.y);
+            }
+        if ((rc = upload(p, &p->zpm, h_zpm))) return bail(rc);
+    }
     if ((rc = upload(p, &p->pair_r, h_pair_r))) return bail(rc);
     if ((rc = upload(p, &p->pair_w, h_pair_w))) return bail(rc);
     if ((rc = upload(p, &p->r_end, h_r_end))) return bail(rc);

@@ -441,7 +441,8 @@ struct ItemWalk {
 template <int N, int NS1>
 __global__ void __launch_bounds__((NS1 + 2) * 128, 1)
 k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
-                const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items,
+                const cplx *__restrict__ zpm, const cplx *__restrict__ twtab,
+                cplx *__restrict__ hyb, int pair0, int n_items,
                 const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
                 cplx *__restrict__ uvw)
 {
@@ -456,8 +457,8 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                   "k_plane_gain_ws is written for N = 64");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *bufs = reinterpret_cast<cplx *>(smem_raw);          // NBUF x (N x PITCH)
-    cplx *phs = bufs + NBUF * N * PITCH;                      // 2 x 3N (S1's phase tables)
-    cplx *tws = phs + 2 * 3 * N;                              // N twiddles exp(+2 pi i t/N)
+    cplx *phs = bufs + NBUF * N * PITCH;                      // 2 x 4N (S1's phase tables: ex, ey, ez, zpm)
+    cplx *tws = phs + 2 * 4 * N;                              // N twiddles exp(+2 pi i t/N)
 
     const int wg = threadIdx.x / GT;
 
@@ -487,9 +488,11 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         // the phase table of item n+1 is copied (cp.async) into the other slot while item n is computed
         auto stage_phase = [&](int it_src, int slot_dst) {
             const cplx *src = phase + (size_t)(pair0 + it_src) * 3 * N;
-            cplx *dstp = phs + slot_dst * 3 * N;
+            cplx *dstp = phs + slot_dst * 4 * N;
             if (ts < 3 * N) cp_async16(dstp + ts, src + ts);
             if (NS1 == 1 && ts + GT < 3 * N) cp_async16(dstp + ts + GT, src + ts + GT);
+            // fourth row: (Re+Im, Re-Im) of the z phase, taken by the last N threads
+            if (ts >= T1 - N) cp_async16(dstp + 3 * N + (ts - (T1 - N)), zpm + (size_t)(pair0 + it_src) * N + (ts - (T1 - N)));
         };
         ItemWalk wk = walk0;                   // plane and item of the current list entry
         if (cnt > 0) stage_phase(wk.it, 0);
@@ -518,10 +521,10 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 bar_sync_n(BAR_S1, T1); // all entries are in registers before anybody overwrites buf
                 cur_plane = i;
             }
-            const cplx *P = phs + slot * 3 * N;
+            const cplx *P = phs + slot * 4 * N;
 
             if (i < N) {
-                // m_H = A (Z.x+Z.y) + B (Z.x-Z.y), see k_plane_gain3
+                // m_H = A (Z.x+Z.y) + B (Z.x-Z.y), see k_plane_gain3; row 3 of P holds the two sums
                 const cplx exi = P[i], eyj = P[N + j];
                 const cplx X = cmul(exi, eyj);
                 const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
@@ -536,8 +539,8 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 #pragma unroll
                     for (int a = 0; a < R; ++a) {
                         const int k = 4 * a + b;
-                        const cplx ez = P[2 * N + k];
-                        const double zp = ez.x + ez.y, zm = ez.x - ez.y;
+                        const cplx zz = P[3 * N + k];
+                        const double zp = zz.x, zm = zz.y;
                         const bool ny = (a == R / 2) && (b == 0); // k == H
                         const double m = (ny ? nA : cA) * zp + (ny ? nB : cB) * zm;
                         const cplx f = fr[u][a];
