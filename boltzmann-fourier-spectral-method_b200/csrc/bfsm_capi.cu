@@ -56,6 +56,7 @@ struct bfsm_plan {
     int plane3 = 1;       // 3-stage / 2-exchange plane kernel (packed mode)
     int plane_ws = 0;     // warp-specialised pipelined plane kernel (packed mode, N = 64): 1 or 2 S1 warpgroups
     int use_side = 1;     // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
+    int nyq_join = 0;     // join the side stream before the next plane kernel starts
     cudaStream_t side = nullptr;
     cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr};
     int pairs_total = 0, pairs_local = 0;
@@ -351,6 +352,12 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                 k_pencil_gain<N, Lc::PG, Lc::PMINB, false>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+        }
+        if (side && p->nyq_join && nyq_pending[ub]) {
+            // the Nyquist accumulate overlaps the (memory-bound) pencil kernel only: the next plane
+            // kernel needs whole SMs and would otherwise start late wherever a side-stream CTA lingers
+            CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
+            nyq_pending[ub] = false;
         }
     }
     for (int ub = 0; ub < 2; ++ub)
@@ -737,8 +744,14 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
         if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk)))
             return bail(rc);
         p->use_side = env_int("BFSM_SIDE_STREAM", 1);
+        p->nyq_join = env_int("BFSM_NYQ_JOIN", 0);
         if (p->use_side) {
-            if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess)
+            // lowest priority: when both streams have CTAs to place, the main stream's kernels go
+            // first and the Nyquist accumulate fills what is left (the pencil kernel's tail)
+            int prio_lo = 0, prio_hi = 0;
+            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+            const int prio = env_int("BFSM_SIDE_LOW_PRIORITY", 0) ? prio_lo : 0;
+            if (cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio) != cudaSuccess)
                 return bail(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
             for (int k = 0; k < 2; ++k) {
                 if (cudaEventCreateWithFlags(&p->ev_plane[k], cudaEventDisableTiming) != cudaSuccess ||

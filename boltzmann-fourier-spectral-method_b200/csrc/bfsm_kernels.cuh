@@ -815,10 +815,16 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
     };
 
     int p = lo;
+    // the pair list is r-major, so the radius segments of [lo,hi) are consecutive radii: only the
+    // first radius index is looked up, and the end of the NEXT segment is fetched one segment ahead
+    // (two dependent global loads per segment and one per pair used to sit on the critical path:
+    // ncu long_scoreboard 29 % of the stall samples)
+    int r = (lo < hi) ? __ldg(&pair_r[pair0 + lo]) : 0;
+    int r_end_cur = (lo < hi) ? __ldg(&r_end[r]) : 0;
     while (p < hi) {
-        const int r = pair_r[pair0 + p];
-        int seg_end = r_end[r] - pair0;
+        int seg_end = r_end_cur - pair0;
         if (seg_end > hi) seg_end = hi;
+        if (seg_end < hi) r_end_cur = __ldg(&r_end[r + 1]); // consumed at the next segment
         // this group's pairs: q_n = p + g + n*PG
         const int n_mine = (seg_end - p - g + PG - 1) / PG;
 #pragma unroll
@@ -828,6 +834,7 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
         }
         for (int n = 0; n < n_mine; ++n) {
             const int q = p + g + n * PG;
+            const double w = __ldg(&pair_w[pair0 + q]); // in flight during the wait and x pass 1
             cp_async_wait<STAGES - 2>();   // this thread's copies for pair n have landed
             group_sync(1 + g, TGP);        // ... and everybody else's; slot (n-1) is free again
             if (n + STAGES - 1 < n_mine) issue(q + (STAGES - 1) * PG, (n + STAGES - 1) % STAGES);
@@ -835,7 +842,6 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
             cplx *sm = ring[g][n % STAGES];
             x1_pass_inplace<N, +1>(sm, tw, tg);
             group_sync(1 + g, TGP);
-            const double w = pair_w[pair0 + q];
 #pragma unroll
             for (int m = 0; m < UNITS; ++m) {
                 cplx v0[B];
@@ -869,6 +875,7 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
         }
         __syncthreads();
         p = seg_end;
+        ++r;
     }
 }
 

@@ -169,6 +169,35 @@ def test_deterministic_and_chunk_independent():
     assert rel_linf(c, a) <= 1e-13
 
 
+@pytest.mark.parametrize("knobs", [{"BFSM_PLANE_WS": "0"}, {"BFSM_PLANE_WS": "2"},
+                                   {"BFSM_PLANE_WS": "0", "BFSM_PLANE3": "0"},
+                                   {"BFSM_ASYNC_PENCIL": "0"}, {"BFSM_SIDE_STREAM": "0"},
+                                   {"BFSM_NYQ_JOIN": "1", "BFSM_SIDE_LOW_PRIORITY": "1"},
+                                   {"BFSM_CHUNK_PAIRS": "7"}],
+                         ids=lambda k: ",".join(f"{a[5:]}={b}" for a, b in k.items()))
+def test_kernel_variants_agree_with_the_oracle(port_oracle, monkeypatch, knobs):
+    """Every selectable kernel variant of the 64^3 path (the warp-specialised pipelined plane kernel
+    with one or two S1 warpgroups = default / BFSM_PLANE_WS=2, the 3-stage and the 4-pass plane
+    kernels, the synchronous pencil kernel, the Nyquist accumulate on the main stream, a chunk size
+    that is not a multiple of the pairs per radius) computes the same Q: each one against the CPU
+    oracle on the non-band-limited input, and against the default variant to a few ulps."""
+    Nv, n_r, n_s = 64, 2, 12
+    f = make_input("noise", Nv)
+    op0, gl, sd = make_operator(Nv, n_r, n_s)
+    assert op0.info()["plane_kernel"] == 2          # k_plane_gain_ws is the default at 64^3
+    q0 = _eval(op0, f)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)                    # tuning knobs are read at plan creation
+    op1, _, _ = make_operator(Nv, n_r, n_s)
+    q1 = _eval(op1, f)
+    q1b = _eval(op1, f)
+    assert np.array_equal(q1, q1b)                  # no atomics in any variant
+    ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    assert rel_linf(q0, ref) <= REL_LINF_TOL
+    assert rel_linf(q1, ref) <= REL_LINF_TOL
+    assert rel_linf(q1, q0) <= 1e-14
+
+
 # ---------------------------------------------------------------- full BASELINE sizes
 FULL = [(64, 32, 192), (32, 16, 94)]
 

@@ -26,6 +26,22 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.bfsm_version() == 100
 
 
+def test_plan_info_mirror_matches_the_header_field_by_field():
+    """The ctypes mirror of bfsm_plan_info must list the header's fields in the same order with the
+    same C types (the library fills the struct through a plain pointer)."""
+    with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
+        header = fh.read()
+    body = re.search(r"typedef struct \{(.*?)\} bfsm_plan_info;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = []
+    for ctype, names in re.findall(r"\b(int|long long)\s+([a-z_0-9, ]+);", body):
+        for name in names.split(","):
+            declared.append((name.strip(), ctype))
+    ctype_of = {ctypes.c_int: "int", ctypes.c_longlong: "long long"}
+    mirrored = [(name, ctype_of[t]) for name, t in capi.PlanInfo._fields_]
+    assert mirrored == declared
+
+
 def _create(lib, nv=(16, 16, 16), n_r=2, n_s=6, shard=(0, 1), L=1.0, null_rho=False):
     dp = ctypes.POINTER(ctypes.c_double)
     rho = np.array([1.0, 2.0][:n_r] + [1.0] * max(0, n_r - 2))
