@@ -4,10 +4,13 @@
 //
 //   f --k_plane<REAL>--> Fh --k_pencil_fwd--> fhat/N^3                     (cpp:168-186)
 //   for chunks of (r,sigma) pairs:                                          (cpp:191-250)
-//       k_plane_gain : fhat plane x separable phase -> 2-D inverse FFT (y,z) of both
-//                      alpha1*fhat and conj(alpha1)*fhat -> hybrid scratch (L2 resident)
-//       k_pencil_gain: inverse FFT along x of both, Re(g1*g2) * w_pair accumulated in
-//                      registers over the chunk's pairs, per-r flush into S_r
+//       plane kernel : fhat plane x separable phase -> 2-D inverse FFT (y,z) -> hybrid scratch
+//                      (unpacked mode: of both alpha1*fhat and conj(alpha1)*fhat).  Three
+//                      implementations: k_plane_gain_ws (64^3 packed mode, default: warp-specialised
+//                      3-stage pipeline), k_plane_gain3 (3 register stages, every warp does all of
+//                      them), k_plane_gain (4 passes; the only one for unpacked mode)
+//       pencil kernel: inverse FFT along x, Re(g1*g2) * w_pair accumulated in registers over the
+//                      chunk's pairs, per-r flush into S_r (k_pencil_gain_async / k_pencil_gain)
 //   S_r --k_plane<REAL>--> Ph_r --k_pencil_accum--> Qhat = sum_r coef_r(|l|^2) FFT3(S_r)
 //                                                                           (cpp:249-273)
 //   Qhat, beta2*fhat --k_plane<FINAL>--> H --k_pencil_final--> Q = Re(Qg) - Re(h) f
@@ -28,8 +31,8 @@
 // with REAL multipliers m_H = c_even + s_odd, n = c_odd + s_even (even/odd under index reversal
 // l -> -l mod N).  n vanishes off the three Nyquist planes, so
 //   Y(v) = (-1)^vx U(vy,vz) + (-1)^vy V(vx,vz) + (-1)^vz W(vx,vy)
-// is assembled from three 2-D transforms per pair (k_plane_nyq) and its square is accumulated by
-// k_nyq_accum.  ONE 3-D transform per pair instead of two, exact for every real input
+// is assembled from three 2-D transforms per pair (the plane kernels' "planes" N, N+1, N+2) and its
+// square is accumulated by k_nyq_accum.  ONE 3-D transform per pair instead of two, exact for every real input
 // (validated against the unpacked path and the oracle with non-band-limited noise input).
 #pragma once
 #include "bfsm_fft.cuh"
