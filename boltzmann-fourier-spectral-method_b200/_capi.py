@@ -18,6 +18,7 @@ EXPORTS = (
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
     "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
     "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host", "bfsm_measure_fp64_peak",
+    "bfsm_debug_plane_work",
 )
 
 KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final", "nyquist")
@@ -80,6 +81,9 @@ def load():
     lib.bfsm_measure_fp64_peak.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     lib.bfsm_plan_set_chunk.restype = ctypes.c_int
     lib.bfsm_plan_set_chunk.argtypes = [vp, ctypes.c_int]
+    ip = ctypes.POINTER(ctypes.c_int)
+    lib.bfsm_debug_plane_work.restype = ctypes.c_int
+    lib.bfsm_debug_plane_work.argtypes = [ctypes.c_int] * 4 + [ip, ip, ctypes.c_int]
     _lib = lib
     return lib
 

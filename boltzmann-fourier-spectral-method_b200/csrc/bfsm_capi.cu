@@ -788,6 +788,35 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     return BFSM_OK;
 }
 
+// Host mirror of the work split of the gain plane kernels (k_plane_gain_ws / k_plane_gain3): the
+// (plane, item) entries CTA `cta` of `n_ctas` walks, in order.  Same range arithmetic as the kernels
+// (first an equal share of the n regular planes, then of the 3 Nyquist planes n..n+2) and the very
+// ItemWalk the pipelined kernel steps with; lets the CPU test suite check that every entry is
+// visited exactly once and that the shares are balanced.
+extern "C" int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, int *planes,
+                                     int *items, int capacity)
+{
+    if (n <= 0 || n_items <= 0 || n_ctas <= 0 || cta < 0 || cta >= n_ctas || capacity < 0 ||
+        (capacity > 0 && (!planes || !items)))
+        return -fail(BFSM_ERR_INVALID, "bfsm_debug_plane_work: bad argument");
+    const long long totA = (long long)n * n_items, totB = (long long)3 * n_items;
+    const int a_lo = (int)((totA * cta) / n_ctas), a_hi = (int)((totA * (cta + 1)) / n_ctas);
+    const int b_lo = (int)((totB * cta) / n_ctas), b_hi = (int)((totB * (cta + 1)) / n_ctas);
+    const int cntA = a_hi - a_lo, cnt = cntA + (b_hi - b_lo);
+    ItemWalk wk;
+    wk.n_items = n_items;
+    wk.iB = n + b_lo / n_items;
+    wk.itB = b_lo % n_items;
+    if (cntA > 0) { wk.i = a_lo / n_items; wk.it = a_lo % n_items; wk.leftA = cntA; }
+    else          { wk.i = wk.iB;          wk.it = wk.itB;         wk.leftA = -1; }
+    for (int k = 0; k < cnt && k < capacity; ++k) {
+        planes[k] = wk.i;
+        items[k] = wk.it;
+        wk.next();
+    }
+    return cnt;
+}
+
 extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
 {
     if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");

@@ -434,7 +434,7 @@ template <int REGS> __device__ __forceinline__ void reg_dealloc()
 // then a second range starting at (iB, itB).
 struct ItemWalk {
     int i, it, n_items, leftA, iB, itB;
-    __device__ __forceinline__ void next()
+    __host__ __device__ __forceinline__ void next()
     {
         if (--leftA == 0) { i = iB; it = itB; }
         else if (++it == n_items) { it = 0; ++i; }

@@ -150,6 +150,13 @@ int bfsm_collide_profiled(bfsm_plan *plan, double *Q_dev, const double *f_dev, v
  * traffic), in fused multiply-adds per second; 2x that is the usual FLOP/s figure. */
 int bfsm_measure_fp64_peak(int device, double *dfma_per_second);
 
+/* Test aid (no device needed): the (plane, item) entries that CTA `cta` of `n_ctas` walks in the gain
+ * plane kernels for a launch of `n_items` pairs on an n^3 grid -- planes 0..n-1 are the regular
+ * (y,z) planes, n..n+2 the three Nyquist planes.  Writes up to `capacity` entries and returns the
+ * CTA's entry count (negative BFSM_ERR_* code on bad arguments). */
+int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, int *planes, int *items,
+                          int capacity);
+
 /* Tuning knob: pairs per launch of the gain kernels (0 = default heuristic). */
 int bfsm_plan_set_chunk(bfsm_plan *plan, int chunk_pairs);
 

@@ -42,6 +42,36 @@ def test_plan_info_mirror_matches_the_header_field_by_field():
     assert mirrored == declared
 
 
+@pytest.mark.parametrize("n,n_items,n_ctas", [(64, 384, 148), (64, 12, 148), (64, 1, 67), (64, 7, 148),
+                                             (32, 752, 296), (16, 24, 592), (64, 383, 132)])
+def test_plane_kernel_work_split_covers_every_entry_once_and_is_balanced(n, n_items, n_ctas):
+    """The gain plane kernels split the flat (plane, item) list so that every CTA gets an equal share of
+    the n regular planes AND of the 3 costlier Nyquist planes (one contiguous range per CTA left the
+    owners of the Nyquist planes 10 % behind).  bfsm_debug_plane_work runs the kernels' range arithmetic
+    and item walker on the host."""
+    lib = capi.load()
+    seen = np.zeros((n + 3, n_items), dtype=np.int32)
+    per_cta = []
+    for cta in range(n_ctas):
+        cap = (n + 3) * n_items
+        planes = (ctypes.c_int * cap)()
+        items = (ctypes.c_int * cap)()
+        cnt = lib.bfsm_debug_plane_work(n, n_items, n_ctas, cta, planes, items, cap)
+        assert 0 <= cnt <= cap
+        pl, it = np.frombuffer(planes, dtype=np.int32)[:cnt], np.frombuffer(items, dtype=np.int32)[:cnt]
+        assert ((0 <= pl) & (pl < n + 3) & (0 <= it) & (it < n_items)).all()
+        np.add.at(seen, (pl, it), 1)
+        per_cta.append((int((pl < n).sum()), int((pl >= n).sum())))
+        # regular entries come first, each class is walked in flat-list order
+        flat = pl.astype(np.int64) * n_items + it
+        assert (np.diff(flat) > 0).all()
+    assert (seen == 1).all()
+    reg = [a for a, _ in per_cta]
+    nyq = [b for _, b in per_cta]
+    assert max(reg) - min(reg) <= 1 and max(nyq) - min(nyq) <= 1
+    assert lib.bfsm_debug_plane_work(n, 0, n_ctas, 0, None, None, 0) == -capi.BFSM_ERR_INVALID
+
+
 def _create(lib, nv=(16, 16, 16), n_r=2, n_s=6, shard=(0, 1), L=1.0, null_rho=False):
     dp = ctypes.POINTER(ctypes.c_double)
     rho = np.array([1.0, 2.0][:n_r] + [1.0] * max(0, n_r - 2))
