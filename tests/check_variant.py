@@ -3,7 +3,9 @@
 relative L-inf difference of Q on maxmix / noise inputs at 64^3 (32 x 192 and 2 x 12), run-to-run
 determinism of the variant, and -- for the small case -- both against the CPU oracle.
 
-    python tools/check_variant.py BFSM_PLANE_WS=1
+    python tests/check_variant.py BFSM_PLANE_WS=1
+
+(lives under tests/: it calls the CPU oracle, which only the test side may do)
 """
 import json
 import os
@@ -11,7 +13,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # helpers.py
 import numpy as np
 import torch
 import bfsm_b200 as B
