@@ -18,7 +18,7 @@ EXPORTS = (
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
     "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
     "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host", "bfsm_measure_fp64_peak",
-    "bfsm_debug_plane_work",
+    "bfsm_debug_plane_work", "bfsm_debug_shares_aligned",
 )
 
 KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final", "nyquist")
@@ -30,6 +30,7 @@ class PlanInfo(ctypes.Structure):
         ("folded", ctypes.c_int), ("packed", ctypes.c_int), ("pairs_total", ctypes.c_int), ("pairs_local", ctypes.c_int),
         ("chunk_pairs", ctypes.c_int), ("launches_per_cell", ctypes.c_int),
         ("scratch_bytes", ctypes.c_longlong), ("plane_kernel", ctypes.c_int),
+        ("partial_slots", ctypes.c_int),
     ]
 
 
@@ -82,6 +83,8 @@ def load():
     lib.bfsm_plan_set_chunk.restype = ctypes.c_int
     lib.bfsm_plan_set_chunk.argtypes = [vp, ctypes.c_int]
     ip = ctypes.POINTER(ctypes.c_int)
+    lib.bfsm_debug_shares_aligned.restype = ctypes.c_int
+    lib.bfsm_debug_shares_aligned.argtypes = [ctypes.c_int] * 5
     lib.bfsm_debug_plane_work.restype = ctypes.c_int
     lib.bfsm_debug_plane_work.argtypes = [ctypes.c_int] * 4 + [ip, ip, ctypes.c_int]
     _lib = lib

@@ -57,6 +57,13 @@ struct bfsm_plan {
     int plane_ws = 0;     // warp-specialised pipelined plane kernel (packed mode, N = 64): 1 or 2 S1 warpgroups
     int use_side = 1;     // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
     int nyq_join = 0;     // join the side stream before the next plane kernel starts
+    // Partial-sum slots: CTA row gy of the pencil / Nyquist kernels owns share gy of a chunk's pairs and,
+    // by default, partial slot gy of S.  When every share of every launch starts at a radius boundary
+    // no two rows touch the same (radius, tile), so one slot per kernel is enough: less to clear, less
+    // for the accumulation stage to read (opt-in: BFSM_ALIGNED_SLOTS=1; decided by update_slot_layout).
+    int aligned_slots = 0;
+    int one_slot_pencil = 0, one_slot_nyq = 0;
+    int n_dir = 0, pair_lo = 0; // pairs per radius; global index of this shard's first pair
     cudaStream_t side = nullptr;
     cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr};
     int pairs_total = 0, pairs_local = 0;
@@ -200,6 +207,9 @@ template <int N> int configure_kernels()
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_async_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pencil_async_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain_smem<N>()));
@@ -252,6 +262,34 @@ struct ProfSpan {
     }
 };
 
+// ---- partial-slot layout ---------------------------------------------------------------------
+// true if, for every launch of `chunk` pairs, the `groups` shares [nc*g/G, nc*(g+1)/G) all start at a
+// radius boundary of the r-major pair list (pair = r*n_dir + d)
+bool shares_start_at_radius_boundaries(int pairs_local, int pair_lo, int n_dir, int chunk, int groups)
+{
+    if (n_dir <= 0 || chunk <= 0) return false;
+    for (int c0 = 0; c0 < pairs_local; c0 += chunk) {
+        const int nc = std::min(chunk, pairs_local - c0);
+        const int G = std::min(groups, nc);
+        for (int g = 1; g < G; ++g) {
+            const int b = (int)(((long long)nc * g) / G);
+            if ((pair_lo + c0 + b) % n_dir != 0) return false;
+        }
+    }
+    return true;
+}
+void update_slot_layout(bfsm_plan *p)
+{
+    const bool on = p->aligned_slots && p->packed && p->async_pencil;
+    auto aligned = [&](int groups) {
+        return shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, groups);
+    };
+    p->one_slot_pencil = (on && p->G > 1 && aligned(p->G)) ? 1 : 0;
+    p->one_slot_nyq = (on && p->GY > 1 && aligned(p->GY)) ? 1 : 0;
+}
+int pencil_slots(const bfsm_plan *p) { return p->one_slot_pencil ? 1 : p->G; }
+int nyq_slots(const bfsm_plan *p) { return !p->packed ? 0 : (p->one_slot_nyq ? 1 : p->GY); }
+
 // ---- one evaluation, split in the two halves the multi-GPU path needs -------------------
 
 // f -> fhat (scaled by 1/N^3) -> partial gain spectrum of this shard
@@ -271,7 +309,7 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     }
 
     // gain: S_r = sum_sigma w Re(g1 g2)
-    const int slots = p->packed ? p->G + p->GY : p->G;
+    const int slots = pencil_slots(p) + nyq_slots(p);
     CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)slots * p->n_r_local * N3, st));
     if (p->packed) {
         ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
@@ -328,9 +366,13 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                 ProfSpan ps(p, ns, BFSM_KCLASS_NYQUIST);
                 const int GY = std::min(p->GY, nc);
                 constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
-                k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
-                    uvw, p->pair_r, p->r_end, p->S + (size_t)p->G * p->n_r_local * N3, c0, nc,
-                    p->n_r_local);
+                double *S2 = p->S + (size_t)pencil_slots(p) * p->n_r_local * N3;
+                if (p->one_slot_nyq)
+                    k_nyq_accum<N, true><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
+                        uvw, p->pair_r, p->r_end, S2, c0, nc, p->n_r_local);
+                else
+                    k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
+                        uvw, p->pair_r, p->r_end, S2, c0, nc, p->n_r_local);
             }
             if (side) {
                 CUDA_TRY(cudaEventRecord(p->ev_nyq[ub], ns));
@@ -340,7 +382,11 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         const int G = std::min(p->G, nc);
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
-            if (p->packed && p->async_pencil)
+            if (p->packed && p->async_pencil && p->one_slot_pencil)
+                k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>
+                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+            else if (p->packed && p->async_pencil)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
@@ -637,6 +683,8 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     const int lo = (int)(((long long)p->pairs_total * shard_index) / shard_count);
     const int hi = (int)(((long long)p->pairs_total * (shard_index + 1)) / shard_count);
     p->pairs_local = hi - lo;
+    p->n_dir = n_dir;
+    p->pair_lo = lo;
 
     // ---- per-pair tables (work list is r-major: pair = r*n_dir + d)
     const int r_first = (p->pairs_local > 0) ? lo / n_dir : 0;
@@ -760,6 +808,8 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
             }
         }
     }
+    p->aligned_slots = env_int("BFSM_ALIGNED_SLOTS", 0);
+    update_slot_layout(p);
     if ((rc = do_configure(p))) return bail(rc);
     *out = p;
     return BFSM_OK;
@@ -817,6 +867,11 @@ extern "C" int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, in
     return cnt;
 }
 
+extern "C" int bfsm_debug_shares_aligned(int pairs_local, int pair_lo, int n_dir, int chunk, int groups)
+{
+    return shares_start_at_radius_boundaries(pairs_local, pair_lo, n_dir, chunk, groups) ? 1 : 0;
+}
+
 extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
 {
     if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
@@ -850,6 +905,7 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
         }
     }
     p->chunk = c;
+    update_slot_layout(p);
     return BFSM_OK;
 }
 
@@ -867,6 +923,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->launches_per_cell = do_launch_count(p);
     info->scratch_bytes = p->scratch_bytes;
     info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : (p->plane3 ? 1 : 0);
+    info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
 }
 

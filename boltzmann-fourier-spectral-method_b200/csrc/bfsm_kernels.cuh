@@ -776,7 +776,9 @@ k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
 // transformed.  Per pair and group: wait for the oldest slot, x pass 1 in place, x pass 2,
 // acc += w (Re^2 - Im^2); two group barriers per pair.
 // ---------------------------------------------------------------------------------------
-template <int N, int PG, int STAGES, int MINB>
+// ONE_SLOT: every CTA row gy accumulates into partial slot 0 -- legal when the gy shares of the chunk
+// start at radius boundaries (then no two CTAs touch the same (radius, tile)); the host checks that.
+template <int N, int PG, int STAGES, int MINB, bool ONE_SLOT = false>
 __global__ void __launch_bounds__(PG *Geo<N>::B *TZ, MINB)
 k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
                     const int *__restrict__ pair_r, const double *__restrict__ pair_w,
@@ -866,7 +868,7 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
                 acc[m][k2] = 0.0;
             }
         __syncthreads();
-        double *Sr = S + ((size_t)blockIdx.y * n_r_local + r) * N3 + tile_off;
+        double *Sr = S + ((size_t)(ONE_SLOT ? 0 : blockIdx.y) * n_r_local + r) * N3 + tile_off;
         for (int e = threadIdx.x; e < TILE; e += PG * TGP) {
             const int x = e / TZ, z = e % TZ;
             const int k1 = x % A, k2 = x / A;
@@ -1079,7 +1081,7 @@ __global__ void k_extract_nyq(const cplx *__restrict__ fhat, cplx *__restrict__ 
 // (even bx, by: the x/y signs are compile-time; the z sign is a per-thread constant).  CTA (tile,gy)
 // covers share gy of the chunk's pairs and owns partial slot gy of S2 -- no atomics.  The 16 x 16
 // slices of U, V, W stream through a 3-stage cp.async ring: one barrier per pair.
-template <int N>
+template <int N, bool ONE_SLOT = false>
 __global__ void __launch_bounds__(256, 2)
 k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
             const int *__restrict__ r_end, double *__restrict__ S2, int pair0, int n_pairs_chunk,
@@ -1152,7 +1154,7 @@ k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
                 }
         }
         cp_async_wait<0>();
-        double *Sr = S2 + ((size_t)blockIdx.y * n_r_local + r) * N3;
+        double *Sr = S2 + ((size_t)(ONE_SLOT ? 0 : blockIdx.y) * n_r_local + r) * N3;
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll

@@ -124,6 +124,7 @@ typedef struct {
     long long scratch_bytes; /* device memory owned by the plan */
     int plane_kernel;        /* gain plane kernel in use: 0 k_plane_gain (4-pass), 1 k_plane_gain3,
                                 2 k_plane_gain_ws (warp-specialised pipeline, 64^3 packed mode) */
+    int partial_slots;       /* partial-sum slots of S_r cleared and summed per evaluation */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);
@@ -156,6 +157,12 @@ int bfsm_measure_fp64_peak(int device, double *dfma_per_second);
  * CTA's entry count (negative BFSM_ERR_* code on bad arguments). */
 int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, int *planes, int *items,
                           int capacity);
+
+/* Test aid (no device needed): 1 if, for every launch of `chunk` pairs over a shard of `pairs_local`
+ * pairs starting at global pair `pair_lo`, the `groups` equal shares of the launch all start at a
+ * radius boundary of the r-major pair list (n_dir pairs per radius) -- the condition under which the
+ * accumulating kernels may share one partial-sum slot (BFSM_ALIGNED_SLOTS=1). */
+int bfsm_debug_shares_aligned(int pairs_local, int pair_lo, int n_dir, int chunk, int groups);
 
 /* Tuning knob: pairs per launch of the gain kernels (0 = default heuristic). */
 int bfsm_plan_set_chunk(bfsm_plan *plan, int chunk_pairs);

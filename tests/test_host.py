@@ -72,6 +72,46 @@ def test_plane_kernel_work_split_covers_every_entry_once_and_is_balanced(n, n_it
     assert lib.bfsm_debug_plane_work(n, 0, n_ctas, 0, None, None, 0) == -capi.BFSM_ERR_INVALID
 
 
+def test_single_slot_condition_matches_a_brute_force_check():
+    """BFSM_ALIGNED_SLOTS=1 lets all CTA rows of the pencil / Nyquist kernels share one partial-sum
+    slot when every row's share of every launch starts at a radius boundary.  The host predicate is
+    checked against a direct enumeration: no radius may be touched by two rows of the same launch."""
+    lib = capi.load()
+
+    def brute(pairs_local, pair_lo, n_dir, chunk, groups):
+        for c0 in range(0, pairs_local, chunk):
+            nc = min(chunk, pairs_local - c0)
+            G = min(groups, nc)
+            owner = {}
+            for g in range(G):
+                for q in range(nc * g // G, nc * (g + 1) // G):
+                    r = (pair_lo + c0 + q) // n_dir
+                    if owner.setdefault(r, g) != g:
+                        return False
+        return True
+
+    cases = [(3072, 0, 96, 384, 4), (384, 768, 96, 384, 4), (752, 0, 47, 1024, 8), (752, 0, 47, 1024, 4),
+             (256, 0, 16, 1024, 8), (768, 0, 24, 1024, 8), (3072, 0, 96, 576, 4), (3072, 0, 96, 7, 4),
+             (1024, 512, 96, 384, 4), (24, 0, 3, 24, 16), (48, 0, 6, 1024, 8)]
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        n_dir = int(rng.integers(1, 50))
+        cases.append((int(rng.integers(1, 400)), int(rng.integers(0, 300)), n_dir,
+                      int(rng.integers(1, 200)), int(rng.integers(1, 9))))
+    n_true = 0
+    for c in cases:
+        got = lib.bfsm_debug_shares_aligned(*c)
+        # the predicate may be conservative (alignment is sufficient, not necessary), never optimistic
+        if got:
+            assert brute(*c), c
+            n_true += 1
+    assert lib.bfsm_debug_shares_aligned(3072, 0, 96, 384, 4) == 1      # cfg 4, one GPU
+    assert lib.bfsm_debug_shares_aligned(384, 1152, 96, 384, 4) == 1    # cfg 4, shard 3 of 8
+    assert lib.bfsm_debug_shares_aligned(752, 0, 47, 1024, 8) == 1      # cfg 5 cell
+    assert lib.bfsm_debug_shares_aligned(3072, 0, 96, 576, 4) == 0
+    assert n_true >= 8
+
+
 def _create(lib, nv=(16, 16, 16), n_r=2, n_s=6, shard=(0, 1), L=1.0, null_rho=False):
     dp = ctypes.POINTER(ctypes.c_double)
     rho = np.array([1.0, 2.0][:n_r] + [1.0] * max(0, n_r - 2))
