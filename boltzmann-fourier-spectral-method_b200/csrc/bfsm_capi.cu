@@ -203,6 +203,12 @@ template <int N> int configure_kernels()
                                       (int)plane_ws_smem<N>()));
         CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)plane_ws_smem<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)plane_ws_smem<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)plane_ws_smem<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)plane_ws_smem<N>()));
     }
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -334,8 +340,18 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             if (N == 64 && p->packed && p->plane_ws) {
                 if constexpr (N == 64) {
                     const int grid = std::min(p->sm_count, (N + 3) * items);
+                    // 2..5: A/B candidates (two S1 warpgroups / other register splits), see WsRegs
                     if (p->plane_ws == 2)
                         k_plane_gain_ws<N, 2><<<grid, 512, plane_ws_smem<N>(), st>>>(
+                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                    else if (p->plane_ws == 3)
+                        k_plane_gain_ws<N, 2, 1><<<grid, 512, plane_ws_smem<N>(), st>>>(
+                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                    else if (p->plane_ws == 4)
+                        k_plane_gain_ws<N, 2, 2><<<grid, 512, plane_ws_smem<N>(), st>>>(
+                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                    else if (p->plane_ws == 5)
+                        k_plane_gain_ws<N, 1, 1><<<grid, 384, plane_ws_smem<N>(), st>>>(
                             p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
                     else
                         k_plane_gain_ws<N, 1><<<grid, 384, plane_ws_smem<N>(), st>>>(

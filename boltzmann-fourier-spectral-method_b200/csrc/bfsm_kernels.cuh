@@ -441,7 +441,16 @@ struct ItemWalk {
     }
 };
 
-template <int N, int NS1>
+// RCFG selects the register split (setmaxnreg targets) among the candidates that compile without
+// spills in the stage loops; RCFG = 0 are the measured defaults, the others are A/B candidates.
+template <int NS1, int RCFG> struct WsRegs;
+template <> struct WsRegs<1, 0> { static constexpr int S1 = 240, S2 = 152, S3 = 112; };
+template <> struct WsRegs<1, 1> { static constexpr int S1 = 232, S2 = 168, S3 = 104; };
+template <> struct WsRegs<2, 0> { static constexpr int S1 = 152, S2 = 104, S3 = 104; };
+template <> struct WsRegs<2, 1> { static constexpr int S1 = 144, S2 = 120, S3 = 104; };
+template <> struct WsRegs<2, 2> { static constexpr int S1 = 152, S2 = 112, S3 = 96; };
+
+template <int N, int NS1, int RCFG = 0>
 __global__ void __launch_bounds__((NS1 + 2) * 128, 1)
 k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 const cplx *__restrict__ zpm, const cplx *__restrict__ twtab,
@@ -454,8 +463,10 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     constexpr int U1 = (4 * N) / T1;      // S1 units (row, residue) per thread and item
     constexpr int U = (4 * N) / GT;       // S2 / S3 units per thread and item
     constexpr int BAR_FULL1 = 1, BAR_FULL2 = 4, BAR_EMPTY = 7, BAR_S1 = 10;
-    constexpr int REG_S1 = NS1 == 1 ? 240 : 152, REG_S2 = NS1 == 1 ? 152 : 104,
-                  REG_S3 = NS1 == 1 ? 112 : 104;
+    constexpr int REG_S1 = WsRegs<NS1, RCFG>::S1, REG_S2 = WsRegs<NS1, RCFG>::S2,
+                  REG_S3 = WsRegs<NS1, RCFG>::S3;
+    static_assert(NS1 * REG_S1 + REG_S2 + REG_S3 <= (NS1 + 2) * (NS1 == 1 ? 168 : 128),
+                  "register targets exceed what the launch allocates");
     static_assert(N == 64 && R == 16 && U == 2 && (NS1 == 1 || NS1 == 2),
                   "k_plane_gain_ws is written for N = 64");
     extern __shared__ __align__(16) unsigned char smem_raw[];

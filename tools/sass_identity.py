@@ -29,7 +29,9 @@ def kernels(so):
         body = [re.sub(r"/\* 0x[0-9a-f]* \*/", "", l).rstrip() for l in f.split("\n")
                 if re.match(r"\s*/\*[0-9a-f]{4,5}\*/", l)]
         name = re.sub(r"_GLOBAL__N__[0-9a-f]+_\d+_(\w+?)_cu_[0-9a-f]{8}", r"_GLOBAL__N_\1_cu", name)  # file hash
-        d[re.sub(r"ELb0EEEv", "EEEv", name)] = body
+        name = re.sub(r"ELb0EEEv", "EEEv", name)               # trailing defaulted `false`
+        name = re.sub(r"(k_plane_gain_wsILi\d+ELi\d+)ELi0EEEv", r"\1EEEv", name)  # ... or defaulted RCFG = 0
+        d[name] = body
     return d
 
 
