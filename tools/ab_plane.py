@@ -17,7 +17,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-DEFAULT_VARIANTS = ["", "BFSM_PLANE_WS=1", "BFSM_PLANE_WS=1 BFSM_CHUNK_PAIRS=1536", "BFSM_CHUNK_PAIRS=1536"]
+DEFAULT_VARIANTS = ["", "BFSM_PLANE_WS=0", "BFSM_PLANE_WS=2"]
+#: candidates written after round 1's GPU budget was spent (compile clean, never run): `all 64 next`
+NEXT_VARIANTS = ["", "BFSM_PLANE_WS=3", "BFSM_PLANE_WS=4", "BFSM_PLANE_WS=5", "BFSM_ALIGNED_SLOTS=1",
+                 "BFSM_ALIGNED_SLOTS=1 BFSM_NYQ_GROUPS=8 BFSM_SIDE_LOW_PRIORITY=1"]
 
 
 def one(Nv, n_r, n_s, ref_path, env, reps=5):
@@ -85,4 +88,7 @@ if __name__ == "__main__":
         one(Nv, n_r, n_s, sys.argv[5], sys.argv[6:])
     else:
         which = sys.argv[2] if len(sys.argv) > 2 else "64"
-        run_all(which, sys.argv[3:] or DEFAULT_VARIANTS)
+        variants = sys.argv[3:] or DEFAULT_VARIANTS
+        if variants == ["next"]:
+            variants = NEXT_VARIANTS
+        run_all(which, variants)
