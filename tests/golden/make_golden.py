@@ -8,6 +8,9 @@ Outputs
   reference_q_vectors.npz   Q = BoltzmannOperator<FFTW_Backend>()(f) for seeded inputs at small
                             configurations, plus the quadrature nodes/weights the reference built
                             (GaussLegendre.hpp / SphericalDesign.cpp), single OpenMP thread.
+  reference_q_64cubed.npz   the same at 64^3 (2 radii x 12-point design), stored as every second point
+                            per axis plus per-plane sums of the full array (`--only-64` writes just
+                            this file)
   bkw_known_answers.json    (a) the L1/L2/Linf errors PUBLISHED in the reference's Results/
                             (file:line cited per entry), (b) the same norms recomputed here with the
                             reference operator at BASELINE.json's (Nv, N_r, N_sigma) combinations.
@@ -44,6 +47,11 @@ PUBLISHED = [  # Results/maxwell_bkw_fftw_atomics.txt, 1-thread runs (N_gl = Nv)
 
 RECOMPUTE = [(16, 8, 6), (16, 16, 6), (32, 16, 32), (32, 16, 48), (32, 32, 12)]
 
+#: 64^3 (the size the pipelined plane kernel serves): every second point per axis (1/8 of the grid,
+#: 256 KB per case) plus per-x-plane sums of Q and Q^2 of the FULL array -> reference_q_64cubed.npz
+SUBSAMPLED_CASES = [(64, 2, 12, "maxmix"), (64, 2, 12, "noise")]
+STRIDE = 2
+
 
 def make_input(kind, Nv):
     if kind == "bkw":
@@ -55,7 +63,7 @@ def make_input(kind, Nv):
 
 def main():
     out = {}
-    for Nv, n_r, n_s, kind in VECTOR_CASES:
+    for Nv, n_r, n_s, kind in ([] if "--only-64" in sys.argv else VECTOR_CASES):
         op = O.ReferenceOperator(Nv, n_r, n_s, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
                                  a=0.0, b=inp.R_SUPPORT, threads=1)
         f = make_input(kind, Nv)
@@ -66,7 +74,24 @@ def main():
         out[f"Nv{Nv}_r{n_r}_s{n_s}_wr"] = w_r
         op.close()
         print("vector", key, float(np.abs(out[key + "_Q"]).max()))
-    np.savez_compressed(os.path.join(HERE, "reference_q_vectors.npz"), **out)
+    if out:
+        np.savez_compressed(os.path.join(HERE, "reference_q_vectors.npz"), **out)
+
+    sub = {"stride": np.array(STRIDE)}
+    for Nv, n_r, n_s, kind in SUBSAMPLED_CASES:
+        op = O.ReferenceOperator(Nv, n_r, n_s, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
+                                 a=0.0, b=inp.R_SUPPORT, threads=1)
+        Q = op(make_input(kind, Nv)).reshape(Nv, Nv, Nv)
+        op.close()
+        key = f"Nv{Nv}_r{n_r}_s{n_s}_{kind}"
+        sub[key + "_Qsub"] = Q[::STRIDE, ::STRIDE, ::STRIDE].copy()
+        sub[key + "_plane_sum"] = Q.sum(axis=(1, 2))
+        sub[key + "_plane_sumsq"] = (Q * Q).sum(axis=(1, 2))
+        sub[key + "_max"] = np.array(np.abs(Q).max())
+        print("subsampled", key, float(np.abs(Q).max()))
+    np.savez_compressed(os.path.join(HERE, "reference_q_64cubed.npz"), **sub)
+    if "--only-64" in sys.argv:
+        return
 
     recomputed = []
     for Nv, n_r, n_s in RECOMPUTE:

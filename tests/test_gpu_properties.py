@@ -41,6 +41,23 @@ def test_matches_reference_golden_vectors(Nv, n_r, n_s, kind):
     assert err <= REL_LINF_TOL, err
 
 
+@pytest.mark.parametrize("kind", ["maxmix", "noise"])
+def test_matches_reference_golden_vectors_at_64_cubed(kind):
+    """The 64^3 path (pipelined plane kernel) against the UNMODIFIED reference operator: every second
+    point per axis elementwise plus per-x-plane sums of Q and Q^2 of the full grid
+    (tests/golden/reference_q_64cubed.npz, make_golden.py --only-64)."""
+    Nv, n_r, n_s = 64, 2, 12
+    G = np.load(os.path.join(ROOT, "tests", "golden", "reference_q_64cubed.npz"))
+    op, _, _ = make_operator(Nv, n_r, n_s)
+    Q = _eval(op, make_input(kind, Nv)).reshape(Nv, Nv, Nv)
+    key, st = f"Nv{Nv}_r{n_r}_s{n_s}_{kind}", int(G["stride"])
+    qmax = float(G[key + "_max"])
+    assert np.abs(Q[::st, ::st, ::st] - G[key + "_Qsub"]).max() / qmax <= REL_LINF_TOL
+    assert np.abs(Q.sum(axis=(1, 2)) - G[key + "_plane_sum"]).max() / (qmax * Nv * Nv) <= REL_LINF_TOL
+    assert (np.abs((Q * Q).sum(axis=(1, 2)) - G[key + "_plane_sumsq"]).max()
+            / (qmax ** 2 * Nv * Nv) <= REL_LINF_TOL)
+
+
 def test_bkw_error_norms_match_published_known_answer():
     """32^3, N_gl=32, 12-point design: Results/maxwell_bkw_fftw_atomics.txt:19-21; north_star asks
     for the BKW error to match the reference's within 1 %."""

@@ -38,6 +38,24 @@ def test_port_matches_reference_golden_vectors(port_oracle, Nv, n_r, n_s, kind):
     assert rel_linf(Q, VECTORS[f"Nv{Nv}_r{n_r}_s{n_s}_{kind}_Q"]) < ORACLE_TOL
 
 
+@pytest.mark.parametrize("kind", ["maxmix", "noise"])
+def test_port_matches_reference_at_64_cubed(port_oracle, kind):
+    """64^3 is where the pipelined plane kernel runs; the GPU parity tests there check against the C
+    port, so the port itself is pinned at that size against the UNMODIFIED reference operator:
+    every second point per axis elementwise, per-x-plane sums of Q and Q^2 for the rest
+    (tests/golden/reference_q_64cubed.npz, written by make_golden.py --only-64)."""
+    Nv, n_r, n_s = 64, 2, 12
+    G = np.load(os.path.join(GOLDEN, "reference_q_64cubed.npz"))
+    gl, sd = quadrature(n_r, n_s)
+    Q = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), make_input(kind, Nv)).reshape(Nv, Nv, Nv)
+    key, st = f"Nv{Nv}_r{n_r}_s{n_s}_{kind}", int(G["stride"])
+    qmax = float(G[key + "_max"])
+    assert np.abs(Q[::st, ::st, ::st] - G[key + "_Qsub"]).max() / qmax < ORACLE_TOL
+    assert np.abs(Q.sum(axis=(1, 2)) - G[key + "_plane_sum"]).max() / (qmax * Nv * Nv) < ORACLE_TOL
+    assert np.abs((Q * Q).sum(axis=(1, 2)) - G[key + "_plane_sumsq"]).max() / (qmax ** 2 * Nv * Nv) < ORACLE_TOL
+    assert abs(np.abs(Q).max() - qmax) / qmax < ORACLE_TOL
+
+
 @pytest.mark.parametrize("kind", ["bkw", "maxmix", "noise"])
 def test_port_matches_numpy_restatement(port_oracle, kind):
     Nv, n_r, n_s = 16, 4, 12
