@@ -70,6 +70,19 @@ def test_bkw_error_norms_match_published_known_answer():
     assert abs(linf - 4.25120273e-05) <= 1e-7 * 4.25120273e-05
 
 
+def test_bkw_error_norms_match_published_known_answer_at_64_cubed():
+    """64^3, N_gl = 64, 12-point design: Results/maxwell_bkw_fftw_atomics.txt:195-197.  The error is
+    ~1e-10 (rounding level of the 768-pair sum), the reference's own runs agree to ~4 digits there;
+    north_star's bar is 1 % (two CPU restatements that differ by 1.7e-15 in Q agree to 2e-4 in L1)."""
+    Nv, n_r, n_s = 64, 64, 12
+    op, _, _ = make_operator(Nv, n_r, n_s)
+    f, Q_exact = inp.bkw(Nv)
+    l1, l2, linf = inp.error_norms(_eval(op, f), Q_exact, Nv)
+    assert abs(l1 - 8.91494353e-11) <= 1e-2 * 8.91494353e-11
+    assert abs(l2 - 8.30921744e-12) <= 1e-2 * 8.30921744e-12
+    assert abs(linf - 3.06852243e-12) <= 1e-2 * 3.06852243e-12
+
+
 def test_folding_is_exact(port_oracle):
     """Antipodal folding (N_sigma/2 transforms, weight x2) against transforming every pair."""
     Nv, n_r, n_s = 16, 4, 12

@@ -93,6 +93,23 @@ def test_port_reproduces_published_bkw_errors(port_oracle, entry):
     assert abs(linf - entry["Linf"]) <= 1e-8 * entry["Linf"]
 
 
+@pytest.mark.parametrize("entry", [e for e in KNOWN["published"] if e["Nv"] == 64],
+                         ids=lambda e: f"Nv{e['Nv']}_Ns{e['N_sigma']}")
+def test_port_reproduces_published_bkw_errors_at_64_cubed(port_oracle, entry):
+    """Results/maxwell_bkw_fftw_atomics.txt:195-197 and :547-549.  At 64^3 the error against the exact
+    BKW derivative is ~1e-10, i.e. rounding noise of the sum over 768 / 2048 pairs is visible from the
+    4th digit on (the reference's own runs differ there), so the bar is north_star's
+    "within 1 %"; observed here: 2e-4 (L1), 1e-6 (L2), 1e-5 (Linf)."""
+    Nv, n_r, n_s = entry["Nv"], entry["N_r"], entry["N_sigma"]
+    gl, sd = quadrature(n_r, n_s)
+    f, Q_exact = inp.bkw(Nv)
+    Q = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    l1, l2, linf = inp.error_norms(Q, Q_exact, Nv)
+    assert abs(l1 - entry["L1"]) <= 1e-2 * entry["L1"]
+    assert abs(l2 - entry["L2"]) <= 1e-2 * entry["L2"]
+    assert abs(linf - entry["Linf"]) <= 1e-2 * entry["Linf"]
+
+
 @pytest.mark.parametrize("entry", [e for e in KNOWN["recomputed"] if e["Nv"] == 16],
                          ids=lambda e: f"Nv{e['Nv']}_Nr{e['N_r']}_Ns{e['N_sigma']}")
 def test_port_reproduces_recomputed_bkw_errors(port_oracle, entry):
