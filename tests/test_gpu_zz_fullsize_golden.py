@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REL_LINF_TOL, make_input, make_operator
+from helpers import REL_LINF_TOL, make_input, make_operator, oracle_args, rel_linf
 
 pytestmark = pytest.mark.gpu
 
@@ -33,3 +33,20 @@ def test_flagship_config_matches_port_oracle_golden(kind):
     assert np.abs(Q.sum(axis=(1, 2)) - GOLD[key + "_plane_sum"]).max() / (qmax * Nv * Nv) <= REL_LINF_TOL
     assert (np.abs((Q * Q).sum(axis=(1, 2)) - GOLD[key + "_plane_sumsq"]).max()
             / (qmax ** 2 * Nv * Nv) <= REL_LINF_TOL)
+
+
+@pytest.mark.parametrize("Nv,n_r,n_s,kind,seed", [(32, 32, 48, "maxmix", 0), (32, 32, 48, "noise", 0),
+                                                  (32, 16, 94, "maxmix", 3), (32, 16, 94, "noise", 1)],
+                         ids=["cfg3-maxmix", "cfg3-noise", "cfg5cell-maxmix", "cfg5cell-noise"])
+def test_32_cubed_baseline_configs_match_the_port_oracle(port_oracle, Nv, n_r, n_s, kind, seed):
+    """BASELINE configs 3 (32^3, 48-point design; N_r = 32 as the stock driver would choose) and 5 (one
+    32^3 cell, 16 x 94) against the C port run live: a few seconds of CPU time each."""
+    op, gl, sd = make_operator(Nv, n_r, n_s)
+    f = make_input(kind, Nv, seed)
+    f_dev = torch.from_numpy(f).cuda().reshape(-1)
+    Q_dev = torch.empty_like(f_dev)
+    op(Q_dev, f_dev)
+    torch.cuda.synchronize()
+    Q_ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    err = rel_linf(Q_dev.cpu().numpy(), Q_ref)
+    assert err <= REL_LINF_TOL, f"relLinf {err:.3e}"
