@@ -159,6 +159,23 @@ def test_no_cpu_fallback_without_a_device():
         op.computeCollision(np.zeros(4096), np.zeros(4096))
 
 
+def test_cpp_driver_fails_loudly_without_a_device():
+    """The C++ operator class (include/B200BoltzmannOperator.hpp) follows the reference's CUDA
+    backend on errors: message on stderr and a non-zero exit status -- never a silent CPU result."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    exe = os.path.join(ROOT, "boltzmann-fourier-spectral-method_b200", "drivers", "build", "maxwell_bkw_b200")
+    designs = os.path.join(ROOT, "oracle", "_ref", "designs")
+    if not (os.path.exists(exe) and os.path.isdir(designs)):
+        pytest.skip("driver or design files not built (python -c 'import __graft_entry__ as g; g.build()')")
+    out = subprocess.run([exe, "--Nv", "16", "--Ns", "6", "-t", "1", "--design-dir", designs],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode != 0
+    assert "no CUDA device available (there is no CPU fallback)" in (out.stdout + out.stderr)
+
+
 def test_gauss_legendre_against_numpy_and_exactness():
     for n in (1, 2, 5, 8, 16, 32, 64):
         gl = B.GaussLegendreQuadrature(n, 0.0, 10.0)
