@@ -117,8 +117,49 @@ template <int SIGN> struct Dft<16, SIGN> {
     }
 };
 
-// Register holding frequency K after Dft<R>::run (natural for R = 4, 8; transposed for 16).
-template <int R> __host__ __device__ constexpr int dft_reg(int K) { return R == 16 ? dft16_reg(K) : K; }
+// exp(SIGN * 2 pi i m / 64) for a compile-time-foldable m (callers unroll their loops): quarter-wave
+// table of cos(2 pi r / 64), r = 0..16, long-double literals.
+template <int SIGN> __device__ __forceinline__ cplx w64(int m)
+{
+    const double C[17] = {1.0, 0.995184726672196886245, 0.980785280403230449126,
+                          0.956940335732208864936, 0.923879532511286756128, 0.881921264348355029713,
+                          0.831469612302545237079, 0.773010453362736960811, 0.707106781186547524401,
+                          0.634393284163645498215, 0.555570233019602224743, 0.471396736825997648556,
+                          0.382683432365089771728, 0.290284677254462367636, 0.195090322016128267848,
+                          0.0980171403295606019942, 0.0};
+    const int q = (m & 63) >> 4, r = m & 15;
+    const double c = C[r], s = C[16 - r];
+    const double wr = q == 0 ? c : q == 1 ? -s : q == 2 ? -c : s;
+    const double wi = q == 0 ? s : q == 1 ? c : q == 2 ? -s : -c;
+    return make_double2(wr, SIGN > 0 ? wi : -wi);
+}
+
+// Radix-32 as 4 x 8, every twiddle a compile-time constant.  Input natural (v[n]); the result is
+// left TRANSPOSED: X[k1 + 4*k2] is in v[8*k1 + k2]; use dft32_reg(K).
+__host__ __device__ constexpr int dft32_reg(int K) { return 8 * (K % 4) + K / 4; }
+
+template <int SIGN> struct Dft<32, SIGN> {
+    static __device__ __forceinline__ void run(cplx (&v)[32])
+    {
+        // pass 1: radix-4 over n1 for each n2 (elements v[8 n1 + n2]); y[k1][n2] -> v[8 k1 + n2]
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) dft4<SIGN>(v[n2], v[8 + n2], v[16 + n2], v[24 + n2]);
+        // twiddles W32^(n2 k1) = W64^(2 n2 k1)
+#pragma unroll
+        for (int k1 = 1; k1 < 4; ++k1)
+#pragma unroll
+            for (int n2 = 1; n2 < 8; ++n2) v[8 * k1 + n2] = cmul(v[8 * k1 + n2], w64<SIGN>(2 * n2 * k1));
+        // pass 2: radix-8 over n2 for each k1; X[k1 + 4 k2] -> v[8 k1 + k2]
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) Dft<8, SIGN>::run(reinterpret_cast<cplx(&)[8]>(v[8 * k1]));
+    }
+};
+
+// Register holding frequency K after Dft<R>::run (natural for R = 4, 8; transposed for 16, 32).
+template <int R> __host__ __device__ constexpr int dft_reg(int K)
+{
+    return R == 32 ? dft32_reg(K) : R == 16 ? dft16_reg(K) : K;
+}
 
 // Pass-1 twiddles of the calling thread: tw[k1-1] = W_N^(SIGN*b*k1), k1 = 1..A-1.
 // twtab[t] = exp(+2 pi i t / N), t in [0,N), tabulated on the host in long double.

@@ -49,7 +49,10 @@ RECOMPUTE = [(16, 8, 6), (16, 16, 6), (32, 16, 32), (32, 16, 48), (32, 32, 12)]
 
 #: 64^3 (the size the pipelined plane kernel serves): every second point per axis (1/8 of the grid,
 #: 256 KB per case) plus per-x-plane sums of Q and Q^2 of the FULL array -> reference_q_64cubed.npz
-SUBSAMPLED_CASES = [(64, 2, 12, "maxmix"), (64, 2, 12, "noise")]
+SUBSAMPLED_CASES = [(64, 2, 12, "maxmix"), (64, 2, 12, "noise"),
+                    # the flagship design itself: ALL 192 directions of ss019.192 with one radius (the
+                    # reference's six batch arrays need 96*64^3*192 = 4.8 GB here, 154.6 GB with 32 radii)
+                    (64, 1, 192, "maxmix"), (64, 1, 192, "noise")]
 STRIDE = 2
 
 
@@ -80,7 +83,7 @@ def main():
     sub = {"stride": np.array(STRIDE)}
     for Nv, n_r, n_s, kind in SUBSAMPLED_CASES:
         op = O.ReferenceOperator(Nv, n_r, n_s, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
-                                 a=0.0, b=inp.R_SUPPORT, threads=1)
+                                 a=0.0, b=inp.R_SUPPORT, threads=(1 if n_s <= 12 else 0))
         Q = op(make_input(kind, Nv)).reshape(Nv, Nv, Nv)
         op.close()
         key = f"Nv{Nv}_r{n_r}_s{n_s}_{kind}"
