@@ -18,7 +18,8 @@ EXPORTS = (
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
     "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
     "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host", "bfsm_measure_fp64_peak",
-    "bfsm_debug_plane_work", "bfsm_debug_shares_aligned",
+    "bfsm_debug_plane_work", "bfsm_debug_shares_aligned", "bfsm_debug_fail_lane_alloc", "bfsm_debug_units",
+    "bfsm_plan_options_init", "bfsm_plan_create_ex",
 )
 
 KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final", "nyquist")
@@ -30,8 +31,45 @@ class PlanInfo(ctypes.Structure):
         ("folded", ctypes.c_int), ("packed", ctypes.c_int), ("pairs_total", ctypes.c_int), ("pairs_local", ctypes.c_int),
         ("chunk_pairs", ctypes.c_int), ("launches_per_cell", ctypes.c_int),
         ("scratch_bytes", ctypes.c_longlong), ("plane_kernel", ctypes.c_int),
-        ("partial_slots", ctypes.c_int),
+        ("partial_slots", ctypes.c_int), ("pencil_kernel", ctypes.c_int),
+        ("batch_lanes_used", ctypes.c_int),
     ]
+
+
+class PlanOptions(ctypes.Structure):
+    """Mirror of bfsm_plan_options (include/bfsm_b200.h); fill with options_from_env() or by hand
+    after bfsm_plan_options_init."""
+    _fields_ = [
+        ("struct_size", ctypes.c_int), ("chunk_pairs", ctypes.c_int), ("pencil_kernel", ctypes.c_int),
+        ("seg_pairs", ctypes.c_int), ("plane_kernel", ctypes.c_int), ("nyq_groups", ctypes.c_int),
+        ("side_stream", ctypes.c_int), ("batch_lanes", ctypes.c_int), ("gain_ctas", ctypes.c_int),
+        ("reserved", ctypes.c_int * 7),
+    ]
+
+
+#: test/tuning override: environment variable -> options field.  The LIBRARY reads no environment
+#: variables; only this Python harness does, so that tools/ab_plane.py and the variant tests can
+#: select kernels per process.
+ENV_OPTIONS = {
+    "BFSM_CHUNK_PAIRS": "chunk_pairs", "BFSM_PENCIL_KERNEL": "pencil_kernel",
+    "BFSM_SEG_PAIRS": "seg_pairs", "BFSM_PLANE_KERNEL": "plane_kernel",
+    "BFSM_NYQ_GROUPS": "nyq_groups", "BFSM_SIDE_STREAM": "side_stream",
+    "BFSM_BATCH_LANES": "batch_lanes", "BFSM_GAIN_CTAS": "gain_ctas",
+}
+
+
+def default_options(**overrides):
+    """bfsm_plan_options with the library defaults, BFSM_* environment overrides, then `overrides`."""
+    opts = PlanOptions()
+    load().bfsm_plan_options_init(ctypes.byref(opts))
+    for env, field in ENV_OPTIONS.items():
+        val = os.environ.get(env)
+        if val not in (None, ""):
+            setattr(opts, field, int(val))
+    for field, val in overrides.items():
+        if val is not None:
+            setattr(opts, field, int(val))
+    return opts
 
 
 class BfsmError(RuntimeError):
@@ -63,6 +101,14 @@ def load():
         ctypes.c_int, dp, dp, ctypes.c_int, dp, dp, dp, dp,
         ctypes.c_double, ctypes.c_double, ctypes.c_double,
         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint]
+    lib.bfsm_plan_create_ex.restype = ctypes.c_int
+    lib.bfsm_plan_create_ex.argtypes = lib.bfsm_plan_create.argtypes + [ctypes.POINTER(PlanOptions)]
+    lib.bfsm_plan_options_init.restype = None
+    lib.bfsm_plan_options_init.argtypes = [ctypes.POINTER(PlanOptions)]
+    lib.bfsm_debug_units.restype = ctypes.c_int
+    lib.bfsm_debug_units.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    lib.bfsm_debug_fail_lane_alloc.restype = ctypes.c_int
+    lib.bfsm_debug_fail_lane_alloc.argtypes = [vp, ctypes.c_int]
     lib.bfsm_plan_destroy.restype = ctypes.c_int
     lib.bfsm_plan_destroy.argtypes = [vp]
     lib.bfsm_collide.restype = ctypes.c_int

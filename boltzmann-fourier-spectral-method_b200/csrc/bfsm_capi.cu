@@ -2,6 +2,7 @@
 // the C ABI declared in include/bfsm_b200.h.  No torch types, no cuFFT, no CPU fallback.
 #include "../../include/bfsm_b200.h"
 #include "bfsm_kernels.cuh"
+#include "bfsm_pencil_reg.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -52,17 +53,24 @@ struct bfsm_plan {
     int folded = 0;
     int packed = 1;   // Hermitian packing: one 3-D transform per pair + Nyquist-plane correction
     int GY = 4;       // pair groups (= S partial slots) of k_nyq_accum
-    int async_pencil = 1; // cp.async ring in the packed pencil kernel
-    int plane3 = 1;       // 3-stage / 2-exchange plane kernel (packed mode)
-    int plane_ws = 0;     // warp-specialised pipelined plane kernel (packed mode, N = 64): 1 or 2 S1 warpgroups
-    int use_side = 1;     // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
-    int nyq_join = 0;     // join the side stream before the next plane kernel starts
-    // Partial-sum slots: CTA row gy of the pencil / Nyquist kernels owns share gy of a chunk's pairs and,
-    // by default, partial slot gy of S.  When every share of every launch starts at a radius boundary
-    // no two rows touch the same (radius, tile), so one slot per kernel is enough: less to clear, less
-    // for the accumulation stage to read (opt-in: BFSM_ALIGNED_SLOTS=1; decided by update_slot_layout).
-    int aligned_slots = 0;
+    int pencil_kernel = 2; // x stage (packed): 1 = staged cp.async ring, 2 = register resident (units)
+    int plane_ws = 0;      // warp-specialised pipelined plane kernel (packed mode, N = 64)
+    int use_side = 1;      // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
+    // Staged x stage and Nyquist accumulate: CTA row gy owns share gy of a chunk's pairs and, in general,
+    // partial slot gy of S.  When every share of every launch starts at a radius boundary no two rows
+    // touch the same (radius, tile), so one slot per kernel is enough (decided by update_slot_layout).
     int one_slot_pencil = 0, one_slot_nyq = 0;
+    // Register-resident x stage: the pair list is cut into work units (<= seg_pairs pairs of one radius
+    // inside one launch); unit k of a radius owns partial slot k of S, written once with plain stores.
+    int seg_pairs = 0, unit_slots = 0, uniform_w = 0;
+    PencilUnit *units = nullptr;  // device copy of h_units
+    int *slots_of_r = nullptr;    // [n_r_local] partial slots radius r uses
+    std::vector<PencilUnit> h_units;
+    std::vector<int> chunk_unit_first; // [n_chunks + 1] first unit of every launch
+    std::vector<double> h_pair_w;
+    int S_slots_capacity = 0;     // partial slots S was allocated for
+    int chunk_capacity = 0;       // pairs the per-chunk scratch (hyb, uvw) was allocated for
+    bfsm_plan_options opt;
     int n_dir = 0, pair_lo = 0; // pairs per radius; global index of this shard's first pair
     cudaStream_t side = nullptr;
     cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr};
@@ -114,9 +122,11 @@ struct bfsm_plan {
     Lane lanes[MAX_LANES];
     cudaEvent_t ev_fork = nullptr;
     int n_lanes = 4; // cells kept in flight in batch mode (1 = strictly sequential)
+    int lane_fail_from = 0; // test hook: allocation of lanes >= this index fails (0 = off)
+    int lanes_used_last = 1; // lanes the last batch call actually ran on
 
     // optional per-kernel-class timing (bfsm_collide_profiled)
-    bool profiling = false;
+    bool profiling = false, profile_failed = false;
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -146,13 +156,6 @@ template <class T> int upload(bfsm_plan *p, T **out, const std::vector<T> &h)
     if (rc) return rc;
     CUDA_TRY(cudaMemcpy(*out, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
     return BFSM_OK;
-}
-
-int env_int(const char *name, int dflt)
-{
-    const char *s = std::getenv(name);
-    if (!s || !*s) return dflt;
-    return std::atoi(s);
 }
 
 // ---- per-N launch geometry ------------------------------------------------------------
@@ -186,11 +189,11 @@ template <int N> size_t plane_ws_smem()
 
 template <int N> size_t pencil_async_smem()
 {
-    // optional padding (tuning knob): a larger request lowers the CTAs/SM of the pencil kernel so
-    // that side-stream kernels can be co-resident
-    static const int pad = env_int("BFSM_PENCIL_SMEM_PAD", 0);
-    return sizeof(cplx) * (size_t)Launch<N>::PG * Launch<N>::PSTAGES * N * TZ + (size_t)pad;
+    return sizeof(cplx) * (size_t)Launch<N>::PG * Launch<N>::PSTAGES * N * TZ;
 }
+
+// register-resident x stage: 8 warps per CTA, two CTAs per SM (128 registers)
+constexpr int PR_WARPS = 8, PR_MINB = 2;
 
 template <int N> int configure_kernels()
 {
@@ -199,15 +202,7 @@ template <int N> int configure_kernels()
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain3_smem<N>()));
     if constexpr (N == 64) {
-        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)plane_ws_smem<N>()));
-        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)plane_ws_smem<N>()));
-        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)plane_ws_smem<N>()));
-        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)plane_ws_smem<N>()));
-        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)plane_ws_smem<N>()));
     }
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
@@ -216,19 +211,12 @@ template <int N> int configure_kernels()
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_async_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>,
+    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)plane_gain_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)plane_gain_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB, false>,
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_gain_smem<N>()));
-    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain<N, Lc::PG, Lc::PMINB, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pencil_gain_smem<N>()));
-
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, -1, PLANE_REAL>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plane_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane<N, +1, PLANE_FINAL>,
@@ -237,11 +225,16 @@ template <int N> int configure_kernels()
 }
 
 // ---- optional CUDA-event bracket around one launch (same stream as the kernel) -----------
+// Profiling must never change the result of a call: an event that cannot be created or recorded
+// switches the profile off for this evaluation (bfsm_collide_profiled then reports the failure).
 cudaEvent_t prof_event(bfsm_plan *p)
 {
     if (p->events_used == p->event_pool.size()) {
-        cudaEvent_t e;
-        cudaEventCreate(&e);
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            p->profile_failed = true;
+            return nullptr;
+        }
         p->event_pool.push_back(e);
     }
     return p->event_pool[p->events_used++];
@@ -255,15 +248,15 @@ struct ProfSpan {
     {
         if (p->profiling) {
             a = prof_event(p);
-            cudaEventRecord(a, st);
+            if (!a || cudaEventRecord(a, st) != cudaSuccess) p->profile_failed = true;
         }
     }
     ~ProfSpan()
     {
         if (p->profiling) {
             cudaEvent_t b = prof_event(p);
-            cudaEventRecord(b, st);
-            p->spans.push_back({cls, a, b});
+            if (!a || !b || cudaEventRecord(b, st) != cudaSuccess) p->profile_failed = true;
+            else p->spans.push_back({cls, a, b});
         }
     }
 };
@@ -284,17 +277,103 @@ bool shares_start_at_radius_boundaries(int pairs_local, int pair_lo, int n_dir, 
     }
     return true;
 }
+// Cuts a shard's pair list (pairs_local pairs starting at global pair pair_lo, n_dir pairs per radius,
+// r-major) into the work units of the register-resident x stage: every launch (chunk) is cut at radius
+// boundaries, every radius segment into pieces of at most seg_pairs pairs; piece k of a radius
+// (counted over the whole shard) owns partial slot k.  Returns the slot count.
+int cut_units(int pairs_local, int pair_lo, int n_dir, int chunk, int seg_pairs,
+              std::vector<PencilUnit> &units, std::vector<int> &chunk_first, std::vector<int> &slots_of_r)
+{
+    units.clear();
+    chunk_first.clear();
+    const int r_first = (pairs_local > 0) ? pair_lo / n_dir : 0;
+    const int r_last = (pairs_local > 0) ? (pair_lo + pairs_local - 1) / n_dir : -1;
+    slots_of_r.assign(std::max(1, r_last - r_first + 1), 0);
+    for (int c0 = 0; c0 < pairs_local; c0 += chunk) {
+        chunk_first.push_back((int)units.size());
+        const int c1 = std::min(pairs_local, c0 + chunk);
+        int q = c0;
+        while (q < c1) {
+            const int r = (pair_lo + q) / n_dir - r_first;            // local radius index
+            const int r_stop = std::min(c1, (r_first + r + 1) * n_dir - pair_lo);
+            const int len = r_stop - q, pieces = (len + seg_pairs - 1) / seg_pairs;
+            for (int k = 0; k < pieces; ++k) {
+                PencilUnit u;
+                u.p0 = q + (int)(((long long)len * k) / pieces);
+                u.p1 = q + (int)(((long long)len * (k + 1)) / pieces);
+                u.r = r;
+                u.slot = slots_of_r[r]++;
+                units.push_back(u);
+            }
+            q = r_stop;
+        }
+    }
+    chunk_first.push_back((int)units.size());
+    int slots = 0;
+    for (int v : slots_of_r) slots = std::max(slots, v);
+    return slots;
+}
+int build_units(bfsm_plan *p, std::vector<int> &slots_of_r)
+{
+    return cut_units(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, p->seg_pairs, p->h_units,
+                     p->chunk_unit_first, slots_of_r);
+}
+
 void update_slot_layout(bfsm_plan *p)
 {
-    const bool on = p->aligned_slots && p->packed && p->async_pencil;
+    const bool staged = p->packed && p->pencil_kernel == 1;
     auto aligned = [&](int groups) {
         return shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, groups);
     };
-    p->one_slot_pencil = (on && p->G > 1 && aligned(p->G)) ? 1 : 0;
-    p->one_slot_nyq = (on && p->GY > 1 && aligned(p->GY)) ? 1 : 0;
+    p->one_slot_pencil = (staged && p->G > 1 && aligned(p->G)) ? 1 : 0;
+    p->one_slot_nyq = (p->packed && p->GY > 1 && aligned(p->GY)) ? 1 : 0;
 }
-int pencil_slots(const bfsm_plan *p) { return p->one_slot_pencil ? 1 : p->G; }
+bool pencil_units_active(const bfsm_plan *p) { return p->packed && p->pencil_kernel == 2; }
+int pencil_slots(const bfsm_plan *p)
+{
+    if (pencil_units_active(p)) return p->unit_slots;
+    return p->one_slot_pencil ? 1 : p->G;
+}
 int nyq_slots(const bfsm_plan *p) { return !p->packed ? 0 : (p->one_slot_nyq ? 1 : p->GY); }
+
+// (re)builds everything that depends on the chunk size: unit table, slot layout, S capacity
+int relayout(bfsm_plan *p)
+{
+    const size_t N3 = (size_t)p->N * p->N * p->N;
+    if (pencil_units_active(p)) {
+        std::vector<int> slots_of_r;
+        p->unit_slots = build_units(p, slots_of_r);
+        if (p->units) { cudaFree(p->units); p->units = nullptr; }
+        if (p->slots_of_r) { cudaFree(p->slots_of_r); p->slots_of_r = nullptr; }
+        const size_t nu = std::max<size_t>(1, p->h_units.size());
+        CUDA_TRY(cudaMalloc((void **)&p->units, nu * sizeof(PencilUnit)));
+        CUDA_TRY(cudaMalloc((void **)&p->slots_of_r, slots_of_r.size() * sizeof(int)));
+        if (!p->h_units.empty())
+            CUDA_TRY(cudaMemcpy(p->units, p->h_units.data(), p->h_units.size() * sizeof(PencilUnit),
+                                cudaMemcpyHostToDevice));
+        CUDA_TRY(cudaMemcpy(p->slots_of_r, slots_of_r.data(), slots_of_r.size() * sizeof(int),
+                            cudaMemcpyHostToDevice));
+    }
+    update_slot_layout(p);
+    const int need = std::max(1, pencil_slots(p) + nyq_slots(p));
+    if (need > p->S_slots_capacity) {
+        if (p->S) {
+            cudaFree(p->S);
+            p->scratch_bytes -= (long long)sizeof(double) * N3 * p->S_slots_capacity * std::max(1, p->n_r_local);
+            p->S = nullptr;
+        }
+        const size_t bytes = sizeof(double) * N3 * (size_t)need * std::max(1, p->n_r_local);
+        cudaError_t e = cudaMalloc((void **)&p->S, bytes);
+        if (e != cudaSuccess) {
+            p->S_slots_capacity = 0;
+            return fail(e == cudaErrorMemoryAllocation ? BFSM_ERR_NOMEM : BFSM_ERR_CUDA,
+                        "cudaMalloc of the partial-sum slots failed");
+        }
+        p->scratch_bytes += (long long)bytes;
+        p->S_slots_capacity = need;
+    }
+    return BFSM_OK;
+}
 
 // ---- one evaluation, split in the two halves the multi-GPU path needs -------------------
 
@@ -314,9 +393,18 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         k_pencil_fwd<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, 1.0 / (double)N3, p->fhat);
     }
 
-    // gain: S_r = sum_sigma w Re(g1 g2)
-    const int slots = pencil_slots(p) + nyq_slots(p);
-    CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)slots * p->n_r_local * N3, st));
+    // gain: S_r = sum_sigma w Re(g1 g2), kept as partial slots that the next stage sums in fixed order.
+    // The register-resident x stage writes each of its slots exactly once (plain stores); the other
+    // accumulating kernels add into theirs, which are cleared first.
+    const bool units = pencil_units_active(p);
+    const int pslots = pencil_slots(p), nslots = nyq_slots(p);
+    const size_t slot_stride = (size_t)p->n_r_local * N3;
+    double *S2 = p->S + (size_t)pslots * slot_stride; // Nyquist slots
+    if (units) {
+        if (nslots) CUDA_TRY(cudaMemsetAsync(S2, 0, sizeof(double) * (size_t)nslots * slot_stride, st));
+    } else {
+        CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)(pslots + nslots) * slot_stride, st));
+    }
     if (p->packed) {
         ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
         k_extract_nyq<N><<<(3 * N * N + 255) / 256, 256, 0, st>>>(p->fhat, p->nyq);
@@ -328,7 +416,7 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         const int nc = std::min(p->chunk, p->pairs_local - c0);
         const int items = p->packed ? nc : 2 * nc;
         const int ub = ci & 1; // uvw buffer of this chunk
-        cplx *uvw = p->packed ? p->uvw + (size_t)ub * 3 * N * N * p->chunk : nullptr;
+        cplx *uvw = p->packed ? p->uvw + (size_t)ub * 3 * N * N * p->chunk_capacity : nullptr;
         if (side && nyq_pending[ub]) { // k_nyq_accum of chunk ci-2 must be done with uvw[ub]
             CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
             nyq_pending[ub] = false;
@@ -340,35 +428,17 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             if (N == 64 && p->packed && p->plane_ws) {
                 if constexpr (N == 64) {
                     const int grid = std::min(p->sm_count, (N + 3) * items);
-                    // 2..5: A/B candidates (two S1 warpgroups / other register splits), see WsRegs
-                    if (p->plane_ws == 2)
-                        k_plane_gain_ws<N, 2><<<grid, 512, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
-                    else if (p->plane_ws == 3)
-                        k_plane_gain_ws<N, 2, 1><<<grid, 512, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
-                    else if (p->plane_ws == 4)
-                        k_plane_gain_ws<N, 2, 2><<<grid, 512, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
-                    else if (p->plane_ws == 5)
-                        k_plane_gain_ws<N, 1, 1><<<grid, 384, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
-                    else
-                        k_plane_gain_ws<N, 1><<<grid, 384, plane_ws_smem<N>(), st>>>(
-                            p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                    k_plane_gain_ws<N><<<grid, 384, plane_ws_smem<N>(), st>>>(
+                        p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
                 }
-            } else if (p->packed && p->plane3)
+            } else if (p->packed)
                 k_plane_gain3<N, Lc::GROUPS, Lc::MINB>
                     <<<ctas, 4 * N * Lc::GROUPS, plane_gain3_smem<N>(), st>>>(
                         p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
-            else if (p->packed)
-                k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, true>
-                    <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
             else
-                k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB, false>
+                k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
                     <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items, nullptr, nullptr, nullptr);
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items);
         }
         if (p->packed) {
             // exact correction for the Nyquist planes: S2_r += sum_s Re(Y_s^2).  FP64-only work,
@@ -382,7 +452,6 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                 ProfSpan ps(p, ns, BFSM_KCLASS_NYQUIST);
                 const int GY = std::min(p->GY, nc);
                 constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
-                double *S2 = p->S + (size_t)pencil_slots(p) * p->n_r_local * N3;
                 if (p->one_slot_nyq)
                     k_nyq_accum<N, true><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
                         uvw, p->pair_r, p->r_end, S2, c0, nc, p->n_r_local);
@@ -398,28 +467,27 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         const int G = std::min(p->G, nc);
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
-            if (p->packed && p->async_pencil && p->one_slot_pencil)
+            if (units) {
+                const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
+                const dim3 grid(PencilGeo<N>::WT / PR_WARPS, nu);
+                if (p->uniform_w)
+                    k_pencil_gain_reg<N, true, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
+                        p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
+                else
+                    k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
+                        p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
+            } else if (p->packed && p->one_slot_pencil)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
-            else if (p->packed && p->async_pencil)
+            else if (p->packed)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
-            else if (p->packed)
-                k_pencil_gain<N, Lc::PG, Lc::PMINB, true>
-                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
-                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
             else
-                k_pencil_gain<N, Lc::PG, Lc::PMINB, false>
+                k_pencil_gain<N, Lc::PG, Lc::PMINB>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
                         p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
-        }
-        if (side && p->nyq_join && nyq_pending[ub]) {
-            // the Nyquist accumulate overlaps the (memory-bound) pencil kernel only: the next plane
-            // kernel needs whole SMs and would otherwise start late wherever a side-stream CTA lingers
-            CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
-            nyq_pending[ub] = false;
         }
     }
     for (int ub = 0; ub < 2; ++ub)
@@ -430,7 +498,8 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         ProfSpan ps(p, st, BFSM_KCLASS_ACCUM);
         if (p->n_r_local > 0) {
             k_plane<N, -1, PLANE_REAL><<<dim3(N, p->n_r_local), N * Geo<N>::B, plane_smem<N>(), st>>>(
-                p->S, slots, (size_t)p->n_r_local * N3, nullptr, nullptr, nullptr, p->tw, p->tmp);
+                p->S, pslots, slot_stride, nullptr, nullptr, nullptr, p->tw, p->tmp,
+                units ? p->slots_of_r : nullptr, S2, nslots);
         }
         k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
     }
@@ -516,8 +585,12 @@ void lanes_free(bfsm_plan *p)
     for (int k = 1; k < bfsm_plan::MAX_LANES; ++k) lane_free(p, k);
 }
 int lane_alloc(bfsm_plan *p, int k);
-int lanes_prepare(bfsm_plan *p)
+// Makes lanes 0 .. want-1 usable (lane 0 is the plan's own scratch) and returns how many are: fewer
+// than `want` when device memory runs out -- the batch then runs with the lanes that exist.
+// `fail_from` (test hook, <= 0 = off) makes the allocation of lane `fail_from` and above fail.
+int lanes_prepare(bfsm_plan *p, int want, int *usable)
 {
+    *usable = 1;
     if (!p->ev_fork) {
         CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
         for (int k = 0; k < bfsm_plan::MAX_LANES; ++k) {
@@ -526,14 +599,16 @@ int lanes_prepare(bfsm_plan *p)
         }
     }
     lane_save(p, 0); // lane 0 == the plan's own scratch
-    for (int k = 1; k < p->n_lanes; ++k) {
-        int rc = lane_alloc(p, k);
+    for (int k = 1; k < want; ++k) {
+        int rc = (p->lane_fail_from > 0 && k >= p->lane_fail_from)
+                     ? fail(BFSM_ERR_NOMEM, "batch lane allocation failure injected by the test hook")
+                     : lane_alloc(p, k);
         if (rc == BFSM_ERR_NOMEM) { // not enough device memory for another lane: run with fewer
             cudaGetLastError();
-            p->n_lanes = k;
             break;
         }
         if (rc) return rc;
+        *usable = k + 1;
     }
     return BFSM_OK;
 }
@@ -566,13 +641,14 @@ int lane_alloc(bfsm_plan *p, int k)
     if ((rc = need((void **)&L.fhat, sizeof(cplx) * N3))) return give_up(rc);
     if ((rc = need((void **)&L.qhat, sizeof(cplx) * N3))) return give_up(rc);
     if ((rc = need((void **)&L.tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local)))) return give_up(rc);
-    if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
+    if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk_capacity)))
         return give_up(rc);
-    if ((rc = need((void **)&L.S, sizeof(double) * N3 * (size_t)(p->G + (p->packed ? p->GY : 0)) * nr)))
+    if ((rc = need((void **)&L.S, sizeof(double) * N3 * (size_t)std::max(1, p->S_slots_capacity) * nr)))
         return give_up(rc);
     if (p->packed) {
         if ((rc = need((void **)&L.nyq, sizeof(cplx) * 3 * N * N))) return give_up(rc);
-        if ((rc = need((void **)&L.uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk))) return give_up(rc);
+        if ((rc = need((void **)&L.uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk_capacity)))
+            return give_up(rc);
         if (p->use_side) {
             if (cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) != cudaSuccess)
                 return give_up(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
@@ -609,13 +685,43 @@ extern "C" int bfsm_version(void) { return BFSM_VERSION; }
 
 extern "C" const char *bfsm_last_error(void) { return g_err.c_str(); }
 
+extern "C" void bfsm_plan_options_init(bfsm_plan_options *o)
+{
+    if (!o) return;
+    std::memset(o, 0, sizeof *o);
+    o->struct_size = (int)sizeof *o;
+    o->side_stream = 1;
+}
+
 extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r,
                                 const double *rho, const double *w_r, int n_s, const double *sx,
                                 const double *sy, const double *sz, const double *w_s,
                                 double gamma, double b_gamma, double L, int device,
                                 int shard_index, int shard_count, unsigned flags)
 {
+    return bfsm_plan_create_ex(out, nvx, nvy, nvz, n_r, rho, w_r, n_s, sx, sy, sz, w_s, gamma, b_gamma, L,
+                               device, shard_index, shard_count, flags, nullptr);
+}
+
+extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r,
+                                   const double *rho, const double *w_r, int n_s, const double *sx,
+                                   const double *sy, const double *sz, const double *w_s,
+                                   double gamma, double b_gamma, double L, int device,
+                                   int shard_index, int shard_count, unsigned flags,
+                                   const bfsm_plan_options *opts)
+{
     if (!out) return fail(BFSM_ERR_INVALID, "out is NULL");
+    bfsm_plan_options opt;
+    bfsm_plan_options_init(&opt);
+    if (opts) {
+        if (opts->struct_size != (int)sizeof opt)
+            return fail(BFSM_ERR_INVALID, "bfsm_plan_options: struct_size mismatch (call bfsm_plan_options_init)");
+        opt = *opts;
+    }
+    if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.nyq_groups < 0 || opt.gain_ctas < 0 ||
+        opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 2 || opt.plane_kernel < 0 ||
+        opt.plane_kernel > 2)
+        return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
     if (!rho || !w_r || !sx || !sy || !sz || !w_s)
         return fail(BFSM_ERR_INVALID, "quadrature pointer is NULL");
@@ -753,14 +859,26 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     }
 
     // ---- launch geometry
+    p->opt = opt;
     int dflt_chunk = (N == 64) ? Launch<64>::CHUNK : (N == 32) ? Launch<32>::CHUNK : Launch<16>::CHUNK;
-    p->chunk = std::max(1, env_int("BFSM_CHUNK_PAIRS", dflt_chunk));
+    p->chunk = opt.chunk_pairs > 0 ? opt.chunk_pairs : dflt_chunk;
     p->chunk = std::min(p->chunk, std::max(1, p->pairs_local));
+    p->chunk_capacity = p->chunk;
     p->G = (N == 64) ? Launch<64>::G : (N == 32) ? Launch<32>::G : Launch<16>::G;
     {
         const int occ = (N == 64) ? 1 : (N == 32) ? 2 : 4;
-        p->gy = std::max(1, env_int("BFSM_GAIN_CTAS", p->sm_count * occ));
+        p->gy = opt.gain_ctas > 0 ? opt.gain_ctas : p->sm_count * occ;
     }
+    p->GY = opt.nyq_groups > 0 ? opt.nyq_groups : (N == 64 ? 4 : (N == 32 ? 8 : 16));
+    p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : 2;
+    p->plane_ws = (N == 64 && opt.plane_kernel != 1) ? 1 : 0;
+    // work units of the register-resident x stage: a quarter of a radius' directions, at most 24 pairs
+    p->seg_pairs = opt.seg_pairs > 0 ? opt.seg_pairs : std::max(1, std::min(24, (n_dir + 3) / 4));
+    p->n_lanes = std::min((int)bfsm_plan::MAX_LANES, opt.batch_lanes > 0 ? opt.batch_lanes : 4);
+    p->use_side = opt.side_stream ? 1 : 0;
+    p->uniform_w = 1;
+    for (double w : rep_w)
+        if (w != rep_w[0]) p->uniform_w = 0;
 
     int rc = BFSM_OK;
     auto bail = [&](int code) {
@@ -791,31 +909,15 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
     if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bail(rc);
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
-    p->GY = std::max(1, env_int("BFSM_NYQ_GROUPS", N == 64 ? 4 : (N == 32 ? 8 : 16)));
-    p->async_pencil = env_int("BFSM_ASYNC_PENCIL", 1);
-    p->plane3 = env_int("BFSM_PLANE3", 1);
-    p->plane_ws = (N == 64) ? env_int("BFSM_PLANE_WS", 1) : 0;
-    p->n_lanes = std::min((int)bfsm_plan::MAX_LANES, std::max(1, env_int("BFSM_BATCH_LANES", 4)));
     if ((rc = dev_alloc(p, (void **)&p->hyb,
                         sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
-        return bail(rc);
-    if ((rc = dev_alloc(p, (void **)&p->S,
-                        sizeof(double) * N3 * (size_t)(p->G + (p->packed ? p->GY : 0)) *
-                            std::max(1, p->n_r_local))))
         return bail(rc);
     if (p->packed) {
         if ((rc = dev_alloc(p, (void **)&p->nyq, sizeof(cplx) * 3 * N * N))) return bail(rc);
         if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk)))
             return bail(rc);
-        p->use_side = env_int("BFSM_SIDE_STREAM", 1);
-        p->nyq_join = env_int("BFSM_NYQ_JOIN", 0);
         if (p->use_side) {
-            // lowest priority: when both streams have CTAs to place, the main stream's kernels go
-            // first and the Nyquist accumulate fills what is left (the pencil kernel's tail)
-            int prio_lo = 0, prio_hi = 0;
-            cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-            const int prio = env_int("BFSM_SIDE_LOW_PRIORITY", 0) ? prio_lo : 0;
-            if (cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, prio) != cudaSuccess)
+            if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess)
                 return bail(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
             for (int k = 0; k < 2; ++k) {
                 if (cudaEventCreateWithFlags(&p->ev_plane[k], cudaEventDisableTiming) != cudaSuccess ||
@@ -824,8 +926,7 @@ extern "C" int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int 
             }
         }
     }
-    p->aligned_slots = env_int("BFSM_ALIGNED_SLOTS", 0);
-    update_slot_layout(p);
+    if ((rc = relayout(p))) return bail(rc); // unit table, slot layout, partial-sum slots S
     if ((rc = do_configure(p))) return bail(rc);
     *out = p;
     return BFSM_OK;
@@ -836,6 +937,9 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     if (!p) return BFSM_OK;
     GuardDevice guard(p->device);
     for (void *q : p->allocs) cudaFree(q);
+    if (p->S) cudaFree(p->S);
+    if (p->units) cudaFree(p->units);
+    if (p->slots_of_r) cudaFree(p->slots_of_r);
     for (cudaEvent_t e : p->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) {
         if (p->ev_plane[k]) cudaEventDestroy(p->ev_plane[k]);
@@ -888,10 +992,40 @@ extern "C" int bfsm_debug_shares_aligned(int pairs_local, int pair_lo, int n_dir
     return shares_start_at_radius_boundaries(pairs_local, pair_lo, n_dir, chunk, groups) ? 1 : 0;
 }
 
+extern "C" int bfsm_debug_units(int pairs_local, int pair_lo, int n_dir, int chunk, int seg_pairs,
+                                int *out, int capacity)
+{
+    if (pairs_local < 0 || pair_lo < 0 || n_dir <= 0 || chunk <= 0 || seg_pairs <= 0 || capacity < 0 ||
+        (capacity > 0 && !out))
+        return -fail(BFSM_ERR_INVALID, "bfsm_debug_units: bad argument");
+    std::vector<PencilUnit> units;
+    std::vector<int> chunk_first, slots_of_r;
+    cut_units(pairs_local, pair_lo, n_dir, chunk, seg_pairs, units, chunk_first, slots_of_r);
+    for (size_t k = 0; k < units.size() && (int)k < capacity; ++k) {
+        out[4 * k + 0] = units[k].p0;
+        out[4 * k + 1] = units[k].p1;
+        out[4 * k + 2] = units[k].r;
+        out[4 * k + 3] = units[k].slot;
+    }
+    return (int)units.size();
+}
+
+extern "C" int bfsm_debug_fail_lane_alloc(bfsm_plan *p, int first_failing_lane)
+{
+    if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
+    GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    CUDA_TRY(cudaDeviceSynchronize());
+    lanes_free(p);
+    p->lane_fail_from = first_failing_lane;
+    return BFSM_OK;
+}
+
 extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
 {
     if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     const int N = p->N;
     const size_t N3 = (size_t)N * N * N;
     int dflt = (N == 64) ? Launch<64>::CHUNK : (N == 32) ? Launch<32>::CHUNK : Launch<16>::CHUNK;
@@ -899,8 +1033,8 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
     c = std::min(c, std::max(1, p->pairs_local));
     CUDA_TRY(cudaDeviceSynchronize());
     lanes_free(p); // re-allocated lazily with the new chunk size
-    if (c > p->chunk) {
-        // grow the per-chunk scratch
+    if (c > p->chunk_capacity) {
+        // grow the per-chunk scratch (never shrunk: the capacity, not the current chunk, is tracked)
         auto regrow = [&](void **slot, size_t bytes_new, size_t bytes_old) -> int {
             void *q = nullptr;
             CUDA_TRY(cudaMalloc(&q, bytes_new));
@@ -912,17 +1046,17 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
             return BFSM_OK;
         };
         const size_t per = sizeof(cplx) * N3 * (p->packed ? 1 : 2);
-        int rc = regrow((void **)&p->hyb, per * c, per * p->chunk);
+        int rc = regrow((void **)&p->hyb, per * c, per * p->chunk_capacity);
         if (rc) return rc;
         if (p->packed) {
             const size_t pern = sizeof(cplx) * 2 * 3 * N * N;
-            rc = regrow((void **)&p->uvw, pern * c, pern * p->chunk);
+            rc = regrow((void **)&p->uvw, pern * c, pern * p->chunk_capacity);
             if (rc) return rc;
         }
+        p->chunk_capacity = c;
     }
     p->chunk = c;
-    update_slot_layout(p);
-    return BFSM_OK;
+    return relayout(p);
 }
 
 extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
@@ -938,7 +1072,9 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->chunk_pairs = p->chunk;
     info->launches_per_cell = do_launch_count(p);
     info->scratch_bytes = p->scratch_bytes;
-    info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : (p->plane3 ? 1 : 0);
+    info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : 1;
+    info->pencil_kernel = !p->packed ? 0 : p->pencil_kernel;
+    info->batch_lanes_used = p->lanes_used_last;
     info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
 }
@@ -947,6 +1083,7 @@ extern "C" int bfsm_gain_hat(bfsm_plan *p, double *Qhat_dev, const double *f_dev
 {
     if (!p || !Qhat_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     return do_gain_hat(p, reinterpret_cast<cplx *>(Qhat_dev), f_dev, (cudaStream_t)stream);
 }
 
@@ -955,6 +1092,7 @@ extern "C" int bfsm_finish(bfsm_plan *p, double *Q_dev, const double *Qhat_dev, 
 {
     if (!p || !Q_dev || !Qhat_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     return do_finish(p, Q_dev, reinterpret_cast<const cplx *>(Qhat_dev), f_dev, (cudaStream_t)stream);
 }
 
@@ -966,12 +1104,16 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
         return fail(BFSM_ERR_INVALID,
                     "bfsm_collide needs an unsharded plan; use bfsm_gain_hat + all-reduce + bfsm_finish");
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     const size_t N3 = (size_t)p->N * p->N * p->N;
     cudaStream_t st = (cudaStream_t)stream;
+    p->lanes_used_last = 1;
     if (n_cells >= 2 && p->n_lanes >= 2 && !p->profiling) {
-        const int nl = std::min(p->n_lanes, n_cells);
-        int rc = lanes_prepare(p);
+        // only as many lanes as there are cells, and only those that could be allocated
+        int nl = 1;
+        int rc = lanes_prepare(p, std::min(p->n_lanes, n_cells), &nl);
         if (rc) return rc;
+        p->lanes_used_last = nl;
         CUDA_TRY(cudaEventRecord(p->ev_fork, st));
         for (int k = 0; k < nl; ++k) CUDA_TRY(cudaStreamWaitEvent(p->lanes[k].main, p->ev_fork, 0));
         for (int c = 0; c < n_cells && !rc; ++c) {
@@ -1004,6 +1146,7 @@ extern "C" int bfsm_collide_host(bfsm_plan *p, double *Q_host, const double *f_h
     if (n_cells < 0) return fail(BFSM_ERR_INVALID, "n_cells must be >= 0");
     if (n_cells == 0) return BFSM_OK;
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     const size_t N3 = (size_t)p->N * p->N * p->N;
     const size_t bytes = sizeof(double) * N3 * (size_t)n_cells;
     if (p->stage_cells < (size_t)n_cells) {
@@ -1030,13 +1173,16 @@ extern "C" int bfsm_collide_profiled(bfsm_plan *p, double *Q_dev, const double *
     if (!p || !Q_dev || !f_dev || !ms_by_class || !launches_by_class)
         return fail(BFSM_ERR_INVALID, "NULL argument");
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
     p->profiling = true;
+    p->profile_failed = false;
     p->spans.clear();
     p->events_used = 0;
     int rc = bfsm_collide(p, Q_dev, f_dev, 1, stream);
     p->profiling = false;
     if (rc) return rc;
+    if (p->profile_failed) return fail(BFSM_ERR_CUDA, "a profiling event could not be created or recorded");
     CUDA_TRY(cudaStreamSynchronize(st));
     for (int c = 0; c < BFSM_KCLASS_COUNT; ++c) {
         ms_by_class[c] = 0.0;
@@ -1055,6 +1201,7 @@ extern "C" int bfsm_sync(bfsm_plan *p, void *stream)
 {
     if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
     GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     return BFSM_OK;
 }

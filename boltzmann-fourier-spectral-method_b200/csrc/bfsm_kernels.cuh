@@ -40,27 +40,18 @@
 namespace bfsm {
 
 // ---------------------------------------------------------------------------------------
-// k_plane_gain: persistent grid (about one CTA per SM slot), block GROUPS*TG.  The flat work
-// list (plane i, item it) with it = 2*pair + array is split evenly over the CTAs; a CTA walks
-// its range plane by plane (reloading the fhat plane when it changes) and its GROUPS groups
-// take the items of a plane alternately.
+// k_plane_gain (UNPACKED mode, BFSM_FLAG_NO_PACK): persistent grid (about one CTA per SM slot),
+// block GROUPS*TG.  The flat work list (plane i, item it) with it = 2*pair + array is split evenly
+// over the CTAs; a CTA walks its range plane by plane (reloading the fhat plane when it changes)
+// and its GROUPS groups take the items of a plane alternately.  Four passes (z1, z2, y1, y2) over a
+// padded plane, see bfsm_fft.cuh.
 // Shared memory: fhat plane (N*N) | GROUPS padded planes (N*ROW) | GROUPS x 2 phase slots (3N).
 // ---------------------------------------------------------------------------------------
-template <int N, int TG, int GROUPS, int MINB, bool PACKED>
+template <int N, int TG, int GROUPS, int MINB>
 __global__ void __launch_bounds__(TG *GROUPS, MINB)
 k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
-             const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items,
-             const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
-             cplx *__restrict__ uvw)
+             const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items)
 {
-    // item -> pair: unpacked items are (pair, array) couples, packed items are pairs
-    constexpr int ISH = PACKED ? 0 : 1;
-    constexpr int H = N / 2;
-    // packed mode appends the three Nyquist planes of fhat as "planes" N, N+1, N+2: plane N+q of
-    // pair p yields uvw[p][q] = sqrt(w_p) IFFT2(n(l) fhat(l)) over the two free axes, where
-    // n = (Re E - Re Et + Im E + Im Et)/2, Et(l) = E(-l); lines shared by two planes are counted
-    // once (plane 1 drops i == H, plane 2 drops i == H and j == H).
-    constexpr int NPL = PACKED ? N + 3 : N;
     constexpr int A = Geo<N>::A, B = Geo<N>::B, ROW = Geo<N>::ROW;
     static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -76,7 +67,7 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     load_twiddles<N, +1>(tw, twtab, tg % B);
 
     // flat work list: index = plane * n_items + item; this CTA owns [w_lo, w_hi)
-    const long long total = (long long)NPL * n_items;
+    const long long total = (long long)N * n_items;
     const int w_lo = (int)((total * blockIdx.x) / gridDim.x);
     const int w_hi = (int)((total * (blockIdx.x + 1)) / gridDim.x);
 
@@ -89,31 +80,22 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 
         __syncthreads(); // every group is done with the previous plane
         {
-            const cplx *srcp = (i < N) ? fhat + (size_t)i * N * N : nyq + (size_t)(i - N) * N * N;
+            const cplx *srcp = fhat + (size_t)i * N * N;
             for (int t = threadIdx.x; t < N * N; t += TG * GROUPS) fpl[t] = srcp[t];
         }
         const int first = it_lo + g;
         if (first < it_hi && tg < 3 * N)
-            myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> ISH)) * 3 * N + tg]);
+            myph[tg] = __ldg(&phase[(size_t)(pair0 + (first >> 1)) * 3 * N + tg]);
         __syncthreads();
 
         int slot = 0;
         for (int it = first; it < it_hi; it += GROUPS, slot ^= 1) {
-            const int arr = PACKED ? 0 : (it & 1);
+            const int arr = it & 1;
             const cplx *P = myph + slot * 3 * N;
             const bool have_next = (it + GROUPS < it_hi) && (tg < 3 * N);
             cplx nxt = make_double2(0.0, 0.0);
-            if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + GROUPS) >> ISH)) * 3 * N + tg]);
-            const cplx exi = P[i < N ? i : 0];
-            // Nyquist-plane items: fixed axis q, free axes (axA, axB) index rows / columns
-            const int nq = i - N;
-            const int axA = (nq == 0) ? 1 : 0, axB = (nq == 2) ? 1 : 2;
-            cplx efix = make_double2(0.0, 0.0);
-            double sw = 0.0;
-            if (PACKED && i >= N) {
-                efix = P[nq * N + H];
-                sw = 0.5 * sqrt(__ldg(&pair_w[pair0 + it]));
-            }
+            if (have_next) nxt = __ldg(&phase[(size_t)(pair0 + ((it + GROUPS) >> 1)) * 3 * N + tg]);
+            const cplx exi = P[i];
 
             // z pass 1 with the phase-weighted load fused in (cpp:198-225):
             // A1 = e^{i theta} fhat, A2 = e^{-i theta} fhat, theta separable in (i,j,k).
@@ -121,63 +103,14 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             for (int u0 = 0; u0 < N * B; u0 += TG) {
                 const int u = u0 + tg;
                 const int j = u / B, b = u % B;
-                const cplx eyj = P[N + j];
-                const cplx exy = cmul(exi, eyj);
+                const cplx exy = cmul(exi, P[N + j]);
                 cplx v[A];
-                if (!PACKED) {
 #pragma unroll
-                    for (int a = 0; a < A; ++a) {
-                        const int k = B * a + b;
-                        const cplx e = cmul(exy, P[2 * N + k]);
-                        const cplx f = fpl[j * N + k];
-                        v[a] = arr ? cmulc(f, e) : cmul(f, e);
-                    }
-                } else if (i >= N) {
-                    const cplx ea = P[axA * N + j];
-                    const cplx eat = (j == H) ? ea : make_double2(ea.x, -ea.y);
-                    const cplx fa = cmul(efix, ea), fat = cmul(efix, eat);
-                    const bool zero_row = (nq >= 1) && (j == H);
-#pragma unroll
-                    for (int a = 0; a < A; ++a) {
-                        const int k = B * a + b;
-                        const cplx eb = P[axB * N + k];
-                        const cplx ebt = (k == H) ? eb : make_double2(eb.x, -eb.y);
-                        const cplx e = cmul(fa, eb), et = cmul(fat, ebt);
-                        double n = sw * ((e.x - et.x) + (e.y + et.y));
-                        if (zero_row || (nq == 2 && k == H)) n = 0.0;
-                        const cplx f = fpl[j * N + k];
-                        v[a] = make_double2(n * f.x, n * f.y);
-                    }
-                } else if (i != H && j != H) {
-                    // interior row: E(-l) = conj(E(l)) except at the z Nyquist column k == H
-#pragma unroll
-                    for (int a = 0; a < A; ++a) {
-                        const int k = B * a + b;
-                        const cplx ez = P[2 * N + k];
-                        const cplx e = cmul(exy, ez);
-                        double m = e.x + e.y;
-                        if (a == H / B && b == 0) { // k == H
-                            const cplx et = cmul(make_double2(exy.x, -exy.y), ez);
-                            m = 0.5 * ((e.x + e.y) + (et.x - et.y));
-                        }
-                        const cplx f = fpl[j * N + k];
-                        v[a] = make_double2(m * f.x, m * f.y);
-                    }
-                } else {
-                    // row on the x or y Nyquist plane: general even/odd split, Et = E(-l)
-                    const cplx ext = (i == H) ? exi : make_double2(exi.x, -exi.y);
-                    const cplx eyt = (j == H) ? eyj : make_double2(eyj.x, -eyj.y);
-                    const cplx exyt = cmul(ext, eyt);
-#pragma unroll
-                    for (int a = 0; a < A; ++a) {
-                        const int k = B * a + b;
-                        const cplx ez = P[2 * N + k];
-                        const cplx ezt = (k == H) ? ez : make_double2(ez.x, -ez.y);
-                        const cplx e = cmul(exy, ez), et = cmul(exyt, ezt);
-                        const double m = 0.5 * ((e.x + e.y) + (et.x - et.y));
-                        const cplx f = fpl[j * N + k];
-                        v[a] = make_double2(m * f.x, m * f.y);
-                    }
+                for (int a = 0; a < A; ++a) {
+                    const int k = B * a + b;
+                    const cplx e = cmul(exy, P[2 * N + k]);
+                    const cplx f = fpl[j * N + k];
+                    v[a] = arr ? cmulc(f, e) : cmul(f, e);
                 }
                 Dft<A, +1>::run(v);
                 cplx *row = buf + j * ROW;
@@ -191,8 +124,7 @@ k_plane_gain(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             if (have_next) myph[(slot ^ 1) * 3 * N + tg] = nxt;
             y1_pass<N, +1, TG>(buf, tw, tg);
             group_sync(1 + g, TG);
-            cplx *dst = (i < N) ? hyb + ((size_t)it * N + i) * N * N
-                                : uvw + ((size_t)it * 3 + nq) * N * N;
+            cplx *dst = hyb + ((size_t)it * N + i) * N * N;
             y2_pass<N, +1, TG>(buf, tg, [&](int y, int z, cplx val) { dst[y * N + z] = val; });
             group_sync(1 + g, TG);
         }
@@ -389,11 +321,11 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 
 // ---------------------------------------------------------------------------------------
 // k_plane_gain_ws (packed mode, N = 64): the three stages of k_plane_gain3 as a WARP-SPECIALISED
-// PIPELINE.  A CTA is NS1 + 2 warpgroups of 128 threads: NS1 for stage S1, one each for S2 and S3;
+// PIPELINE.  A CTA is three warpgroups of 128 threads, one per stage S1, S2, S3;
 // every warpgroup walks the CTA's whole item list and item n lives in plane buffer n % 3 on its
 // way through the stages:
 //
-//   S1 warpgroup(s): keep their entries of the fhat plane IN REGISTERS for as long as the plane does
+//   S1 warpgroup: keeps its entries of the fhat plane IN REGISTERS for as long as the plane does
 //       not change (no per-item re-read of fhat from shared memory), apply the real multiplier m_H,
 //       radix-16 along z, store rows                                       -> full1[buf]
 //   S2 warpgroup: 4 x 4 blocks in place (both twiddles)                    -> full2[buf]
@@ -408,8 +340,9 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 // warpgroups' own barrier (phase-table and plane staging).  S3 releases a buffer only after the
 // global stores that depend on its loads, so a buffer cannot be overwritten under an outstanding
 // LDS.  Registers move between the warpgroups with setmaxnreg:
-//   NS1 = 1: 384 threads launched at 168 -> S1 240 | S2 152 | S3 112      (2 units per S1 thread)
-//   NS1 = 2: 512 threads launched at 128 -> S1 2 x 152 | S2 104 | S3 104  (1 unit per S1 thread)
+//   384 threads launched at 168 -> S1 240 | S2 152 | S3 112      (2 units per S1 thread)
+// (two S1 warpgroups at 512 threads and three other register splits were measured 2.3-5 % slower:
+// profiles/r02_ab64_next.log).
 // The arithmetic is that of k_plane_gain3 (same formulas, same operation order; the results agree
 // to the last bit or two -- the compiler contracts a few multiply-adds differently).
 // ---------------------------------------------------------------------------------------
@@ -441,17 +374,11 @@ struct ItemWalk {
     }
 };
 
-// RCFG selects the register split (setmaxnreg targets) among the candidates that compile without
-// spills in the stage loops; RCFG = 0 are the measured defaults, the others are A/B candidates.
-template <int NS1, int RCFG> struct WsRegs;
-template <> struct WsRegs<1, 0> { static constexpr int S1 = 240, S2 = 152, S3 = 112; };
-template <> struct WsRegs<1, 1> { static constexpr int S1 = 232, S2 = 168, S3 = 104; };
-template <> struct WsRegs<2, 0> { static constexpr int S1 = 152, S2 = 104, S3 = 104; };
-template <> struct WsRegs<2, 1> { static constexpr int S1 = 144, S2 = 120, S3 = 104; };
-template <> struct WsRegs<2, 2> { static constexpr int S1 = 152, S2 = 112, S3 = 96; };
+// register targets (setmaxnreg) of the three warpgroups; 384 threads launched at 168
+struct WsRegs { static constexpr int S1 = 240, S2 = 152, S3 = 112; };
 
-template <int N, int NS1, int RCFG = 0>
-__global__ void __launch_bounds__((NS1 + 2) * 128, 1)
+template <int N>
+__global__ void __launch_bounds__(3 * 128, 1)
 k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 const cplx *__restrict__ zpm, const cplx *__restrict__ twtab,
                 cplx *__restrict__ hyb, int pair0, int n_items,
@@ -459,16 +386,13 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 cplx *__restrict__ uvw)
 {
     constexpr int R = N / 4, GT = 128, PITCH = N + 1, H = N / 2, NPL = N + 3, NBUF = 3;
-    constexpr int T1 = NS1 * GT;          // threads of stage S1
+    constexpr int T1 = GT;                // threads of stage S1
     constexpr int U1 = (4 * N) / T1;      // S1 units (row, residue) per thread and item
     constexpr int U = (4 * N) / GT;       // S2 / S3 units per thread and item
     constexpr int BAR_FULL1 = 1, BAR_FULL2 = 4, BAR_EMPTY = 7, BAR_S1 = 10;
-    constexpr int REG_S1 = WsRegs<NS1, RCFG>::S1, REG_S2 = WsRegs<NS1, RCFG>::S2,
-                  REG_S3 = WsRegs<NS1, RCFG>::S3;
-    static_assert(NS1 * REG_S1 + REG_S2 + REG_S3 <= (NS1 + 2) * (NS1 == 1 ? 168 : 128),
-                  "register targets exceed what the launch allocates");
-    static_assert(N == 64 && R == 16 && U == 2 && (NS1 == 1 || NS1 == 2),
-                  "k_plane_gain_ws is written for N = 64");
+    constexpr int REG_S1 = WsRegs::S1, REG_S2 = WsRegs::S2, REG_S3 = WsRegs::S3;
+    static_assert(REG_S1 + REG_S2 + REG_S3 <= 3 * 168, "register targets exceed what the launch allocates");
+    static_assert(N == 64 && R == 16 && U == 2, "k_plane_gain_ws is written for N = 64");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *bufs = reinterpret_cast<cplx *>(smem_raw);          // NBUF x (N x PITCH)
     cplx *phs = bufs + NBUF * N * PITCH;                      // 2 x 4N (S1's phase tables: ex, ey, ez, zpm)
@@ -492,7 +416,7 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     if (threadIdx.x < N) tws[threadIdx.x] = __ldg(&twtab[threadIdx.x]);
     __syncthreads();
 
-    if (wg < NS1) {
+    if (wg == 0) {
         // =========================== S1: phase-weighted fhat, radix-R along z ===================
         reg_alloc<REG_S1>();
         const int ts = threadIdx.x;            // 0 .. T1-1
@@ -504,7 +428,7 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             const cplx *src = phase + (size_t)(pair0 + it_src) * 3 * N;
             cplx *dstp = phs + slot_dst * 4 * N;
             if (ts < 3 * N) cp_async16(dstp + ts, src + ts);
-            if (NS1 == 1 && ts + GT < 3 * N) cp_async16(dstp + ts + GT, src + ts + GT);
+            if (ts + GT < 3 * N) cp_async16(dstp + ts + GT, src + ts + GT);
             // fourth row: (Re+Im, Re-Im) of the z phase, taken by the last N threads
             if (ts >= T1 - N) cp_async16(dstp + 3 * N + (ts - (T1 - N)), zpm + (size_t)(pair0 + it_src) * N + (ts - (T1 - N)));
         };
@@ -605,10 +529,10 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         // absorb S3's releases of the last items so that every barrier ends balanced
         for (int n = (cnt > NBUF ? cnt - NBUF : 0); n < cnt; ++n)
             bar_sync_n(BAR_EMPTY + n % NBUF, T1 + GT);
-    } else if (wg == NS1) {
+    } else if (wg == 1) {
         // =========================== S2: 4 x 4 blocks in place ===================================
         reg_dealloc<REG_S2>();
-        const int t = threadIdx.x - NS1 * GT;
+        const int t = threadIdx.x - GT;
         // unit q = t + 128 u: b' = q % R = t % R, k1 = q / R = t / R + 8 u
         const int s2b = t % R;
         cplx wy[3];
@@ -653,7 +577,7 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     } else {
         // =========================== S3: radix-R along y, natural-order store ====================
         reg_dealloc<REG_S3>();
-        const int t = threadIdx.x - (NS1 + 1) * GT;
+        const int t = threadIdx.x - 2 * GT;
         // unit q = t + 128 u: column slot q % N = t % N, k1' = q / N = t / N + 2 u
         const int s3slot = t % N;
         int buf_id = 0;
@@ -682,13 +606,13 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
 }
 
 // ---------------------------------------------------------------------------------------
-// k_pencil_gain: grid (N*N/TZ tiles, G), block PG*(B*TZ).  CTA (tile, gy) owns chunk pairs
-// [lo,hi) = share gy of the chunk; its PG groups take them round-robin.  Each group:
+// k_pencil_gain (UNPACKED mode): grid (N*N/TZ tiles, G), block PG*(B*TZ).  CTA (tile, gy) owns chunk
+// pairs [lo,hi) = share gy of the chunk; its PG groups take them round-robin.  Each group:
 // inverse x-FFT of g1' and g2' pencils, acc += w * Re(g1 g2) (cpp:233-246 + linearity of
 // the forward FFT).  At every change of radius r the PG partial sums are reduced through
 // shared memory in fixed order and added to S[gy][r] -- no atomics, deterministic.
 // ---------------------------------------------------------------------------------------
-template <int N, int PG, int MINB, bool PACKED>
+template <int N, int PG, int MINB>
 __global__ void __launch_bounds__(PG *Geo<N>::B *TZ, MINB)
 k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
               const int *__restrict__ pair_r, const double *__restrict__ pair_w,
@@ -724,33 +648,19 @@ k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
         if (seg_end > hi) seg_end = hi;
         for (int q = p + g; q < seg_end; q += PG) {
             const double w = pair_w[pair0 + q];
-            if (PACKED) {
-                const cplx *zh = hyb + (size_t)q * N3 + tile_off;
-                x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return zh[(size_t)x * N * N + z]; });
-                group_sync(1 + g, TGP);
+            const cplx *g1 = hyb + (size_t)(2 * q) * N3 + tile_off;
+            const cplx *g2 = g1 + N3;
+            x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return g1[(size_t)x * N * N + z]; });
+            x1_pass<N, +1>(sm[g][1], tw, tg, [&](int x, int z) { return g2[(size_t)x * N * N + z]; });
+            group_sync(1 + g, TGP);
 #pragma unroll
-                for (int m = 0; m < UNITS; ++m) {
-                    cplx v0[B];
-                    x2_unit<N, +1>(sm[g][0], tg, m, v0);
+            for (int m = 0; m < UNITS; ++m) {
+                cplx v0[B], v1[B];
+                x2_unit<N, +1>(sm[g][0], tg, m, v0);
+                x2_unit<N, +1>(sm[g][1], tg, m, v1);
 #pragma unroll
-                    for (int k2 = 0; k2 < B; ++k2)
-                        acc[m][k2] += w * (v0[k2].x * v0[k2].x - v0[k2].y * v0[k2].y);
-                }
-            } else {
-                const cplx *g1 = hyb + (size_t)(2 * q) * N3 + tile_off;
-                const cplx *g2 = g1 + N3;
-                x1_pass<N, +1>(sm[g][0], tw, tg, [&](int x, int z) { return g1[(size_t)x * N * N + z]; });
-                x1_pass<N, +1>(sm[g][1], tw, tg, [&](int x, int z) { return g2[(size_t)x * N * N + z]; });
-                group_sync(1 + g, TGP);
-#pragma unroll
-                for (int m = 0; m < UNITS; ++m) {
-                    cplx v0[B], v1[B];
-                    x2_unit<N, +1>(sm[g][0], tg, m, v0);
-                    x2_unit<N, +1>(sm[g][1], tg, m, v1);
-#pragma unroll
-                    for (int k2 = 0; k2 < B; ++k2)
-                        acc[m][k2] += w * (v0[k2].x * v1[k2].x - v0[k2].y * v1[k2].y);
-                }
+                for (int k2 = 0; k2 < B; ++k2)
+                    acc[m][k2] += w * (v0[k2].x * v1[k2].x - v0[k2].y * v1[k2].y);
             }
             group_sync(1 + g, TGP);
         }
@@ -907,7 +817,9 @@ template <int N, int SIGN, int MODE>
 __global__ void __launch_bounds__(N *Geo<N>::B)
 k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stride,
         const cplx *__restrict__ qhat, const cplx *__restrict__ fhat,
-        const double *__restrict__ beta2, const cplx *__restrict__ twtab, cplx *__restrict__ dst)
+        const double *__restrict__ beta2, const cplx *__restrict__ twtab, cplx *__restrict__ dst,
+        const int *__restrict__ n_partials_item = nullptr, const double *__restrict__ src_real2 = nullptr,
+        int n_partials2 = 0)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B, TG = N * B;
     constexpr size_t N3 = (size_t)N * N * N;
@@ -919,10 +831,15 @@ k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stri
     load_twiddles<N, SIGN>(tw, twtab, tg % B);
 
     if (MODE == PLANE_REAL) {
+        // fixed-order sum of the partial slots: `n_partials` (or this item's own count) slots of
+        // src_real, then n_partials2 slots of src_real2
         const double *s = src_real + (size_t)item * N3 + (size_t)i * N * N;
+        const double *s2 = src_real2 + (size_t)item * N3 + (size_t)i * N * N;
+        const int np = n_partials_item ? __ldg(&n_partials_item[item]) : n_partials;
         z1_pass<N, SIGN, TG>(buf, tw, tg, [&](int j, int k) {
             double v = 0.0;
-            for (int gq = 0; gq < n_partials; ++gq) v += s[(size_t)gq * partial_stride + j * N + k];
+            for (int gq = 0; gq < np; ++gq) v += s[(size_t)gq * partial_stride + j * N + k];
+            for (int gq = 0; gq < n_partials2; ++gq) v += s2[(size_t)gq * partial_stride + j * N + k];
             return make_double2(v, 0.0);
         });
     } else {

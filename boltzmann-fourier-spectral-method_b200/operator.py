@@ -24,7 +24,7 @@ def _torch():
 
 class BoltzmannOperatorB200:
     def __init__(self, gl_quadrature, spherical_quadrature, Nvx, Nvy, Nvz, gamma, b_gamma, L,
-                 device=None, shard_index=0, shard_count=1, fold=True, pack=True):
+                 device=None, shard_index=0, shard_count=1, fold=True, pack=True, options=None):
         # like the reference constructors: store arguments only
         self.gl_quadrature = gl_quadrature
         self.spherical_quadrature = spherical_quadrature
@@ -34,6 +34,8 @@ class BoltzmannOperatorB200:
         self.shard_index, self.shard_count = int(shard_index), int(shard_count)
         self.fold = bool(fold)
         self.pack = bool(pack)
+        #: dict of bfsm_plan_options fields (chunk_pairs, pencil_kernel, ...); None = defaults
+        self.options = dict(options or {})
         self._plan = None
         self._lib = None
 
@@ -49,7 +51,8 @@ class BoltzmannOperatorB200:
         if dev is None:
             dev = torch.cuda.current_device()
         elif not isinstance(dev, int):
-            dev = torch.device(dev).index or 0
+            idx = torch.device(dev).index
+            dev = torch.cuda.current_device() if idx is None else idx   # 'cuda' = the current device
         self.device = int(dev)
 
         def arr(v):
@@ -61,13 +64,15 @@ class BoltzmannOperatorB200:
         w_s = arr(self.spherical_quadrature.getWeights())
         dp = ctypes.POINTER(ctypes.c_double)
         plan = ctypes.c_void_p()
-        rc = lib.bfsm_plan_create(
+        opts = _capi.default_options(**self.options)
+        rc = lib.bfsm_plan_create_ex(
             ctypes.byref(plan), self.Nvx, self.Nvy, self.Nvz,
             len(rho), rho.ctypes.data_as(dp), w_r.ctypes.data_as(dp),
             len(sx), sx.ctypes.data_as(dp), sy.ctypes.data_as(dp), sz.ctypes.data_as(dp),
             w_s.ctypes.data_as(dp), self.gamma, self.b_gamma, self.L, self.device,
             self.shard_index, self.shard_count,
-            (0 if self.fold else _capi.BFSM_FLAG_NO_FOLD) | (0 if self.pack else _capi.BFSM_FLAG_NO_PACK))
+            (0 if self.fold else _capi.BFSM_FLAG_NO_FOLD) | (0 if self.pack else _capi.BFSM_FLAG_NO_PACK),
+            ctypes.byref(opts))
         _capi.check(rc)
         self._plan = plan
         self._lib = lib
@@ -131,6 +136,11 @@ class BoltzmannOperatorB200:
         if isinstance(f_in, torch.Tensor) and f_in.is_cuda:
             if n_cells is None:
                 n_cells = f_in.numel() // N
+                if n_cells < 1 or f_in.numel() != n_cells * N:
+                    raise ValueError(f"f_in has {f_in.numel()} elements: not a positive multiple of "
+                                     f"the grid size {N}")
+            if n_cells < 0:
+                raise ValueError("n_cells must be >= 0")   # an explicit 0 is an empty batch: no-op
             self._check_dev(f_in, n_cells * N, "f_in")
             self._check_dev(Q, n_cells * N, "Q")
             rc = self._lib.bfsm_collide(self._plan, ctypes.c_void_p(Q.data_ptr()),

@@ -71,6 +71,36 @@ int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r, const 
                      const double *sz, const double *w_s, double gamma, double b_gamma, double L,
                      int device, int shard_index, int shard_count, unsigned flags);
 
+/*
+ * Tuning options of a plan (all optional: bfsm_plan_create uses the defaults).  Fill the struct with
+ * bfsm_plan_options_init() first, change what you need, pass it to bfsm_plan_create_ex().  The library
+ * reads NO environment variables; the Python test harness maps BFSM_* variables onto this struct.
+ */
+typedef struct {
+    int struct_size;       /* = sizeof(bfsm_plan_options), set by bfsm_plan_options_init */
+    int chunk_pairs;       /* pairs per launch of the gain kernels; 0 = heuristic */
+    int pencil_kernel;     /* x stage (packed mode): 0 = default, 1 = staged through a cp.async ring in
+                              shared memory, 2 = register resident (no shared memory, LDG + SHFL) */
+    int seg_pairs;         /* register-resident x stage: pairs per work unit (one partial slot each);
+                              0 = heuristic */
+    int plane_kernel;      /* (y,z) stage (packed mode): 0 = default, 1 = k_plane_gain3 (every warp runs
+                              all three stages), 2 = k_plane_gain_ws (warp-specialised pipeline, 64^3) */
+    int nyq_groups;        /* pair groups (= partial slots) of the Nyquist accumulate; 0 = heuristic */
+    int side_stream;       /* 1: Nyquist accumulate on an internal side stream (default), 0: in line */
+    int batch_lanes;       /* cells kept in flight by bfsm_collide(n_cells > 1): 1..4, 0 = default (4) */
+    int gain_ctas;         /* persistent CTAs of k_plane_gain3; 0 = SMs x occupancy */
+    int reserved[7];
+} bfsm_plan_options;
+
+void bfsm_plan_options_init(bfsm_plan_options *opts);
+
+/* bfsm_plan_create with explicit options (NULL = defaults). */
+int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r, const double *rho,
+                        const double *w_r, int n_s, const double *sx, const double *sy,
+                        const double *sz, const double *w_s, double gamma, double b_gamma, double L,
+                        int device, int shard_index, int shard_count, unsigned flags,
+                        const bfsm_plan_options *opts);
+
 /* Replaces ~BoltzmannOperator() (FFTWBoltzmannOperator.cpp:338-363). NULL is accepted. */
 int bfsm_plan_destroy(bfsm_plan *plan);
 
@@ -122,9 +152,12 @@ typedef struct {
     int chunk_pairs;         /* pairs per gain-kernel launch */
     int launches_per_cell;   /* kernel launches issued per evaluated cell */
     long long scratch_bytes; /* device memory owned by the plan */
-    int plane_kernel;        /* gain plane kernel in use: 0 k_plane_gain (4-pass), 1 k_plane_gain3,
-                                2 k_plane_gain_ws (warp-specialised pipeline, 64^3 packed mode) */
-    int partial_slots;       /* partial-sum slots of S_r cleared and summed per evaluation */
+    int plane_kernel;        /* gain plane kernel in use: 0 k_plane_gain (4-pass, unpacked mode),
+                                1 k_plane_gain3, 2 k_plane_gain_ws (warp-specialised pipeline, 64^3) */
+    int partial_slots;       /* partial-sum slots of S_r summed per evaluation */
+    int pencil_kernel;       /* x stage in use: 0 k_pencil_gain (unpacked mode), 1 k_pencil_gain_async
+                                (cp.async ring), 2 k_pencil_gain_reg (register resident) */
+    int batch_lanes_used;    /* lanes the last bfsm_collide(n_cells > 1) ran on (1 before any) */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);
@@ -161,8 +194,20 @@ int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, int *planes, 
 /* Test aid (no device needed): 1 if, for every launch of `chunk` pairs over a shard of `pairs_local`
  * pairs starting at global pair `pair_lo`, the `groups` equal shares of the launch all start at a
  * radius boundary of the r-major pair list (n_dir pairs per radius) -- the condition under which the
- * accumulating kernels may share one partial-sum slot (BFSM_ALIGNED_SLOTS=1). */
+ * staged x stage and the Nyquist accumulate share one partial-sum slot per kernel. */
 int bfsm_debug_shares_aligned(int pairs_local, int pair_lo, int n_dir, int chunk, int groups);
+
+/* Test aid (no device needed): the work units the register-resident x stage cuts a shard's pair list
+ * into (see bfsm_plan_options.seg_pairs): out[4k .. 4k+3] = {first pair, one past the last pair, local
+ * radius index, partial slot} of unit k, pairs counted from the shard's first pair.  Every unit lies
+ * inside one launch (chunk) and one radius.  Writes up to `capacity` units, returns the unit count
+ * (negative BFSM_ERR_* code on bad arguments). */
+int bfsm_debug_units(int pairs_local, int pair_lo, int n_dir, int chunk, int seg_pairs, int *out,
+                     int capacity);
+
+/* Test aid: makes the allocation of batch lanes >= `first_failing_lane` fail with BFSM_ERR_NOMEM
+ * (0 = off), to exercise the "run with the lanes that exist" path of bfsm_collide(n_cells > 1). */
+int bfsm_debug_fail_lane_alloc(bfsm_plan *plan, int first_failing_lane);
 
 /* Tuning knob: pairs per launch of the gain kernels (0 = default heuristic). */
 int bfsm_plan_set_chunk(bfsm_plan *plan, int chunk_pairs);

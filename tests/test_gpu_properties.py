@@ -12,6 +12,8 @@ import bfsm_b200 as B
 from helpers import REL_LINF_TOL, inp, make_input, make_operator, oracle_args, quadrature, rel_linf
 from oracle import oracle as O
 
+capi = B.submodule("_capi")
+
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -199,60 +201,83 @@ def test_deterministic_and_chunk_independent():
     assert rel_linf(c, a) <= 1e-13
 
 
-@pytest.mark.parametrize("knobs", [{"BFSM_PLANE_WS": "0"}, {"BFSM_PLANE_WS": "2"},
-                                   {"BFSM_PLANE_WS": "0", "BFSM_PLANE3": "0"},
-                                   {"BFSM_ASYNC_PENCIL": "0"}, {"BFSM_SIDE_STREAM": "0"},
-                                   {"BFSM_NYQ_JOIN": "1", "BFSM_SIDE_LOW_PRIORITY": "1"},
-                                   {"BFSM_CHUNK_PAIRS": "7"}],
-                         ids=lambda k: ",".join(f"{a[5:]}={b}" for a, b in k.items()))
-def test_kernel_variants_agree_with_the_oracle(port_oracle, monkeypatch, knobs):
-    """Every selectable kernel variant of the 64^3 path (the warp-specialised pipelined plane kernel
-    with one or two S1 warpgroups = default / BFSM_PLANE_WS=2, the 3-stage and the 4-pass plane
-    kernels, the synchronous pencil kernel, the Nyquist accumulate on the main stream, a chunk size
-    that is not a multiple of the pairs per radius) computes the same Q: each one against the CPU
-    oracle on the non-band-limited input, and against the default variant to a few ulps."""
+@pytest.mark.parametrize("knobs", [{"plane_kernel": 1}, {"pencil_kernel": 1}, {"pencil_kernel": 1, "plane_kernel": 1},
+                                   {"seg_pairs": 5}, {"side_stream": 0}, {"chunk_pairs": 7},
+                                   {"chunk_pairs": 7, "pencil_kernel": 1}, {"nyq_groups": 3}],
+                         ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
+def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
+    """Every selectable kernel variant of the 64^3 path (bfsm_plan_options: the warp-specialised
+    pipelined plane kernel = default vs the 3-stage plane kernel, the register-resident x stage =
+    default vs the cp.async-staged one, odd work-unit sizes, the Nyquist accumulate on the main
+    stream, a chunk size that is not a multiple of the pairs per radius) computes the same Q: each one
+    against the CPU oracle on the non-band-limited input, and against the default variant to a few
+    ulps.  No variant uses atomics: repeated evaluations are bitwise identical."""
     Nv, n_r, n_s = 64, 2, 12
     f = make_input("noise", Nv)
     op0, gl, sd = make_operator(Nv, n_r, n_s)
     assert op0.info()["plane_kernel"] == 2          # k_plane_gain_ws is the default at 64^3
+    assert op0.info()["pencil_kernel"] == 2         # k_pencil_gain_reg is the default x stage
     q0 = _eval(op0, f)
-    for k, v in knobs.items():
-        monkeypatch.setenv(k, v)                    # tuning knobs are read at plan creation
-    op1, _, _ = make_operator(Nv, n_r, n_s)
+    op1, _, _ = make_operator(Nv, n_r, n_s, options=knobs)
+    for key, val in knobs.items():
+        if key in ("plane_kernel", "pencil_kernel"):
+            assert op1.info()[key] == val
     q1 = _eval(op1, f)
     q1b = _eval(op1, f)
-    assert np.array_equal(q1, q1b)                  # no atomics in any variant
+    assert np.array_equal(q1, q1b)
     ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
     assert rel_linf(q0, ref) <= REL_LINF_TOL
     assert rel_linf(q1, ref) <= REL_LINF_TOL
     assert rel_linf(q1, q0) <= 1e-14
 
 
-#: opt-in code paths written after the round's GPU budget was spent: they compile and their host logic
-#: is tested on the CPU, but they have not run on a GPU yet.  Enable with BFSM_TEST_EXPERIMENTAL=1.
-EXPERIMENTAL = os.environ.get("BFSM_TEST_EXPERIMENTAL") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="not validated on a GPU yet: set BFSM_TEST_EXPERIMENTAL=1")
 @pytest.mark.parametrize("Nv,n_r,n_s", [(32, 16, 32), (64, 4, 12), (16, 8, 6)])
-def test_aligned_single_slot_accumulation_is_bitwise_neutral(monkeypatch, Nv, n_r, n_s):
-    """BFSM_ALIGNED_SLOTS=1: when every CTA row's share of a launch starts at a radius boundary the
-    pencil and Nyquist kernels accumulate into one partial slot each instead of one per row.  The
-    slots that are dropped only ever held zeros for the radii in question, so Q must not change by a
-    single bit; the plan reports 2 slots instead of G + GY."""
+@pytest.mark.parametrize("pencil_kernel", [1, 2])
+def test_slot_layouts_follow_the_chunking(port_oracle, Nv, n_r, n_s, pencil_kernel):
+    """Partial-sum slots: the staged x stage and the Nyquist accumulate share ONE slot each whenever
+    every CTA row's share of every launch starts at a radius boundary, and fall back to one slot per
+    row otherwise; the register-resident x stage owns one slot per work unit of a radius.  Changing
+    the chunk size re-cuts the units; Q stays within rounding of the first layout and of the oracle."""
     f = make_input("noise", Nv)
-    op0, _, _ = make_operator(Nv, n_r, n_s)
-    q0 = _eval(op0, f)
-    monkeypatch.setenv("BFSM_ALIGNED_SLOTS", "1")
-    op1, _, _ = make_operator(Nv, n_r, n_s)
-    assert op1.info()["partial_slots"] <= op0.info()["partial_slots"]
-    if Nv == 32:
-        assert op1.info()["partial_slots"] == 2
-    q1 = _eval(op1, f)
-    assert np.array_equal(q0, q1)
-    op1.set_chunk(5)                       # shares no longer aligned: falls back to one slot per row
-    assert op1.info()["partial_slots"] == op0.info()["partial_slots"]
-    assert rel_linf(_eval(op1, f), q0) <= 1e-13
+    op, gl, sd = make_operator(Nv, n_r, n_s, options={"pencil_kernel": pencil_kernel})
+    slots0 = op.info()["partial_slots"]
+    q0 = _eval(op, f)
+    ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    assert rel_linf(q0, ref) <= REL_LINF_TOL
+    op.set_chunk(5)                        # shares / units no longer aligned with the radii
+    assert op.info()["partial_slots"] >= slots0 or pencil_kernel == 2
+    q1 = _eval(op, f)
+    assert rel_linf(q1, q0) <= 1e-13
+    op.set_chunk(0)                        # back to the default: the first layout again, bit for bit
+    assert op.info()["partial_slots"] == slots0
+    assert np.array_equal(_eval(op, f), q0)
+
+
+def test_batch_runs_with_fewer_lanes_when_lane_memory_is_short():
+    """bfsm_collide(n_cells > 1) keeps up to four cells in flight on lanes with their own scratch; when
+    a lane cannot be allocated (BFSM_ERR_NOMEM, injected here) the batch runs on the lanes that exist
+    instead of touching unallocated scratch, and gives the same Q bit for bit."""
+    Nv, n_r, n_s, cells = 16, 8, 6, 5
+    op, _, _ = make_operator(Nv, n_r, n_s)
+    lib = capi.load()
+    f = np.stack([make_input("maxmix", Nv, c) for c in range(cells)]).reshape(-1)
+    f_dev = torch.from_numpy(f).cuda()
+    q_dev = torch.empty_like(f_dev)
+    op(q_dev, f_dev, n_cells=cells)
+    torch.cuda.synchronize()
+    q_all = q_dev.cpu().numpy().copy()
+    assert op.info()["batch_lanes_used"] == 4
+    for fail_from, expect in ((2, 2), (1, 1), (3, 3)):
+        capi.check(lib.bfsm_debug_fail_lane_alloc(op._plan, fail_from))
+        q_dev.zero_()
+        op(q_dev, f_dev, n_cells=cells)
+        torch.cuda.synchronize()
+        assert op.info()["batch_lanes_used"] == expect
+        assert np.array_equal(q_dev.cpu().numpy(), q_all)
+    capi.check(lib.bfsm_debug_fail_lane_alloc(op._plan, 0))
+    op(q_dev, f_dev, n_cells=2)            # only as many lanes as cells
+    torch.cuda.synchronize()
+    assert op.info()["batch_lanes_used"] == 2
 
 
 # ---------------------------------------------------------------- full BASELINE sizes

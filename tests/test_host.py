@@ -31,7 +31,7 @@ def test_plan_info_mirror_matches_the_header_field_by_field():
     same C types (the library fills the struct through a plain pointer)."""
     with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
         header = fh.read()
-    body = re.search(r"typedef struct \{(.*?)\} bfsm_plan_info;", header, re.S).group(1)
+    body = re.search(r"typedef struct \{([^{}]*)\} bfsm_plan_info;", header, re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     declared = []
     for ctype, names in re.findall(r"\b(int|long long)\s+([a-z_0-9, ]+);", body):
@@ -40,6 +40,59 @@ def test_plan_info_mirror_matches_the_header_field_by_field():
     ctype_of = {ctypes.c_int: "int", ctypes.c_longlong: "long long"}
     mirrored = [(name, ctype_of[t]) for name, t in capi.PlanInfo._fields_]
     assert mirrored == declared
+
+
+def test_plan_options_mirror_matches_the_header_field_by_field():
+    """Same for bfsm_plan_options (the Python harness fills it, the library reads it)."""
+    with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
+        header = fh.read()
+    body = re.search(r"typedef struct \{([^{}]*)\} bfsm_plan_options;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    declared = []
+    for name, dim in re.findall(r"\bint\s+([a-z_0-9]+)(?:\[(\d+)\])?;", body):
+        declared.append((name, int(dim) if dim else 1))
+    mirrored = [(name, 1 if t is ctypes.c_int else t._length_) for name, t in capi.PlanOptions._fields_]
+    assert mirrored == declared
+    opts = capi.PlanOptions()
+    capi.load().bfsm_plan_options_init(ctypes.byref(opts))
+    assert opts.struct_size == ctypes.sizeof(capi.PlanOptions) and opts.side_stream == 1
+
+
+def test_library_reads_no_environment_variables():
+    """Tuning goes through bfsm_plan_options; the library sources must not call getenv (a stray
+    variable used to change the product path silently).  The statically linked CUDA runtime does
+    reference getenv, so the check is on our sources, not on the symbol table."""
+    csrc = os.path.join(ROOT, "boltzmann-fourier-spectral-method_b200", "csrc")
+    for name in os.listdir(csrc):
+        if name.endswith((".cu", ".cuh", ".hpp", ".h")):
+            with open(os.path.join(csrc, name)) as fh:
+                assert "getenv" not in fh.read(), name
+
+
+@pytest.mark.parametrize("pairs_local,pair_lo,n_dir,chunk,seg", [
+    (3072, 0, 96, 384, 24), (384, 768, 96, 384, 24), (752, 0, 47, 1024, 12), (3072, 0, 96, 7, 24),
+    (1024, 512, 96, 384, 5), (24, 0, 3, 24, 1), (48, 0, 6, 1024, 24), (100, 37, 16, 33, 6), (0, 0, 8, 16, 4)])
+def test_work_units_of_the_register_x_stage_tile_the_pair_list(pairs_local, pair_lo, n_dir, chunk, seg):
+    """bfsm_debug_units runs the host code that cuts a shard's pair list into work units: the units
+    tile [0, pairs_local) in order, none crosses a launch (chunk) or a radius boundary or exceeds
+    seg_pairs, and within a radius the slots are 0, 1, 2, ... (each (slot, radius) written once)."""
+    lib = capi.load()
+    cap = max(1, pairs_local)
+    out = (ctypes.c_int * (4 * cap))()
+    n = lib.bfsm_debug_units(pairs_local, pair_lo, n_dir, chunk, seg, out, cap)
+    assert 0 <= n <= cap
+    units = [tuple(out[4 * k:4 * k + 4]) for k in range(n)]
+    pos, seen = 0, {}
+    r_first = pair_lo // n_dir
+    for p0, p1, r, slot in units:
+        assert p0 == pos and p0 < p1 <= p0 + seg
+        assert p0 // chunk == (p1 - 1) // chunk
+        assert (pair_lo + p0) // n_dir - r_first == r == (pair_lo + p1 - 1) // n_dir - r_first
+        assert slot == seen.get(r, 0)
+        seen[r] = slot + 1
+        pos = p1
+    assert pos == pairs_local
+    assert lib.bfsm_debug_units(10, 0, 0, 4, 2, None, 0) == -capi.BFSM_ERR_INVALID
 
 
 @pytest.mark.parametrize("n,n_items,n_ctas", [(64, 384, 148), (64, 12, 148), (64, 1, 67), (64, 7, 148),
