@@ -3,6 +3,7 @@
 #include "../../include/bfsm_b200.h"
 #include "bfsm_kernels.cuh"
 #include "bfsm_pencil_reg.cuh"
+#include "bfsm_fused.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -68,6 +69,14 @@ struct bfsm_plan {
     std::vector<PencilUnit> h_units;
     std::vector<int> chunk_unit_first; // [n_chunks + 1] first unit of every launch
     std::vector<double> h_pair_w;
+    // fused persistent gain kernel (64^3 packed mode): roles, sub-chunk size, ring depth
+    int fused = 0, fused_K = 0, fused_D = 0, fused_NQ = 0, fused_NN = 0;
+    int *sync_flags = nullptr;    // [2 * n_sub] ready / consumed counters of the fused kernel
+    // split pipeline: the plane kernel of chunk c+1 (on split_ctas SMs) runs next to the x stage of
+    // chunk c (second stream, the remaining SMs); two hybrid scratch buffers
+    int split = 0, split_ctas = 0;
+    cudaStream_t xs = nullptr;
+    cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_hyb[2] = {nullptr, nullptr};
     int S_slots_capacity = 0;     // partial slots S was allocated for
     int chunk_capacity = 0;       // pairs the per-chunk scratch (hyb, uvw) was allocated for
     bfsm_plan_options opt;
@@ -114,6 +123,7 @@ struct bfsm_plan {
         cplx *fhat = nullptr, *tmp = nullptr, *hyb = nullptr, *nyq = nullptr, *uvw = nullptr,
              *qhat = nullptr;
         double *S = nullptr;
+        int *sync_flags = nullptr;
         cudaStream_t main = nullptr, side = nullptr;
         cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr}, done = nullptr;
         bool allocated = false;
@@ -127,6 +137,7 @@ struct bfsm_plan {
 
     // optional per-kernel-class timing (bfsm_collide_profiled)
     bool profiling = false, profile_failed = false;
+    bool profiling_serial = false; // batch lanes: scratch of lanes >= 1 has no second hybrid buffer
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -203,6 +214,10 @@ template <int N> int configure_kernels()
                                   (int)plane_gain3_smem<N>()));
     if constexpr (N == 64) {
         CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_ws<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)plane_ws_smem<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_gain_fused<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)plane_ws_smem<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_gain_fused<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)plane_ws_smem<N>()));
     }
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
@@ -315,20 +330,32 @@ int cut_units(int pairs_local, int pair_lo, int n_dir, int chunk, int seg_pairs,
 }
 int build_units(bfsm_plan *p, std::vector<int> &slots_of_r)
 {
+    // fused kernel: one launch over all pairs, units = the radius pieces of every sub-chunk
+    if (p->fused)
+        return cut_units(p->pairs_local, p->pair_lo, p->n_dir, p->fused_K, p->fused_K, p->h_units,
+                         p->chunk_unit_first, slots_of_r);
     return cut_units(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, p->seg_pairs, p->h_units,
                      p->chunk_unit_first, slots_of_r);
 }
 
 void update_slot_layout(bfsm_plan *p)
 {
-    const bool staged = p->packed && p->pencil_kernel == 1;
+    const bool staged = p->packed && p->pencil_kernel == 1 && !p->fused;
     auto aligned = [&](int groups) {
         return shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, groups);
     };
     p->one_slot_pencil = (staged && p->G > 1 && aligned(p->G)) ? 1 : 0;
     p->one_slot_nyq = (p->packed && p->GY > 1 && aligned(p->GY)) ? 1 : 0;
 }
-bool pencil_units_active(const bfsm_plan *p) { return p->packed && p->pencil_kernel == 2; }
+bool pencil_units_active(const bfsm_plan *p) { return p->packed && (p->pencil_kernel == 2 || p->fused); }
+// hybrid grids / Nyquist-field sets the per-launch scratch holds
+size_t hyb_grids(const bfsm_plan *p)
+{
+    if (p->fused) return (size_t)p->fused_D * p->fused_K;
+    return (size_t)(p->packed ? 1 : 2) * p->chunk_capacity * (p->split ? 2 : 1);
+}
+size_t uvw_sets(const bfsm_plan *p) { return p->fused ? (size_t)std::max(1, p->pairs_local) : (size_t)2 * p->chunk_capacity; }
+int fused_subs(const bfsm_plan *p) { return (p->pairs_local + p->fused_K - 1) / std::max(1, p->fused_K); }
 int pencil_slots(const bfsm_plan *p)
 {
     if (pencil_units_active(p)) return p->unit_slots;
@@ -409,14 +436,62 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
         k_extract_nyq<N><<<(3 * N * N + 255) / 256, 256, 0, st>>>(p->fhat, p->nyq);
     }
+    if (p->fused) {
+        if constexpr (N == 64) {
+            const int n_sub = fused_subs(p);
+            CUDA_TRY(cudaMemsetAsync(p->sync_flags, 0, sizeof(int) * 2 * (size_t)n_sub, st));
+            FusedParams fp;
+            fp.n_nyq = p->fused_NN;
+            fp.n_pencil = p->fused_NQ;
+            fp.n_plane = p->sm_count - fp.n_nyq - fp.n_pencil;
+            fp.pair0 = 0;
+            fp.n_pairs = p->pairs_local;
+            fp.n_units = (int)p->h_units.size();
+            fp.rs.ready = p->sync_flags;
+            fp.rs.consumed = p->sync_flags + n_sub;
+            fp.rs.n_sub = n_sub;
+            fp.rs.ring = p->fused_D;
+            fp.rs.sub_pairs = p->fused_K;
+            fp.rs.n_pairs = p->pairs_local;
+            fp.rs.tiles = PencilGeo<N>::WT;
+            const cplx *fhat = p->fhat, *phase = p->phase, *zpm = p->zpm, *tw = p->tw, *nyqp = p->nyq;
+            cplx *ring = p->hyb, *uvw = p->uvw;
+            const double *pw = p->pair_w;
+            const PencilUnit *un = p->units;
+            double *Sp = p->S;
+            int nrl = p->n_r_local;
+            void *args[] = {&fp, &fhat, &phase, &zpm, &tw, &ring, &nyqp, &pw, &uvw, &un, &Sp, &nrl};
+            {
+                ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
+                const void *fn = p->uniform_w ? (const void *)k_gain_fused<N, true> : (const void *)k_gain_fused<N, false>;
+                CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3(fp.n_plane + fp.n_nyq + fp.n_pencil),
+                                                     dim3(FUSED_THREADS), args, plane_ws_smem<N>(), st));
+            }
+            {
+                ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
+                const int GY = std::min(p->GY, p->pairs_local);
+                constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
+                if (p->one_slot_nyq)
+                    k_nyq_accum<N, true><<<dim3(NYQ_TILES, GY), 256, 0, st>>>(
+                        p->uvw, p->pair_r, p->r_end, S2, 0, p->pairs_local, p->n_r_local);
+                else
+                    k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, st>>>(
+                        p->uvw, p->pair_r, p->r_end, S2, 0, p->pairs_local, p->n_r_local);
+            }
+        }
+    }
     int ci = 0;
     bool nyq_pending[2] = {false, false};
     const bool side = p->packed && p->use_side && p->side;
-    for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk, ++ci) {
+    for (int c0 = 0; c0 < p->pairs_local && !p->fused; c0 += p->chunk, ++ci) {
         const int nc = std::min(p->chunk, p->pairs_local - c0);
         const int items = p->packed ? nc : 2 * nc;
         const int ub = ci & 1; // uvw buffer of this chunk
         cplx *uvw = p->packed ? p->uvw + (size_t)ub * 3 * N * N * p->chunk_capacity : nullptr;
+        // split pipeline: chunk ci uses hybrid buffer ci & 1, free once the x stage of chunk ci-2 is done
+        const bool split = p->split && p->xs && !p->profiling_serial;
+        cplx *hyb = p->hyb + (split ? (size_t)ub * N3 * p->chunk_capacity : 0);
+        if (split && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_x[ub], 0));
         if (side && nyq_pending[ub]) { // k_nyq_accum of chunk ci-2 must be done with uvw[ub]
             CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
             nyq_pending[ub] = false;
@@ -427,14 +502,14 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
             if (N == 64 && p->packed && p->plane_ws) {
                 if constexpr (N == 64) {
-                    const int grid = std::min(p->sm_count, (N + 3) * items);
+                    const int grid = std::min(split ? p->split_ctas : p->sm_count, (N + 3) * items);
                     k_plane_gain_ws<N><<<grid, 384, plane_ws_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                        p->fhat, p->phase, p->zpm, p->tw, hyb, c0, items, p->nyq, p->pair_w, uvw);
                 }
             } else if (p->packed)
                 k_plane_gain3<N, Lc::GROUPS, Lc::MINB>
                     <<<ctas, 4 * N * Lc::GROUPS, plane_gain3_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                        p->fhat, p->phase, p->tw, hyb, c0, items, p->nyq, p->pair_w, uvw);
             else
                 k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
                     <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
@@ -465,17 +540,24 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             }
         }
         const int G = std::min(p->G, nc);
+        // split pipeline: the x stage of this chunk goes to the second stream, behind the plane kernel
+        cudaStream_t xst = split ? p->xs : st;
+        if (split) {
+            CUDA_TRY(cudaEventRecord(p->ev_hyb[ub], st));
+            CUDA_TRY(cudaStreamWaitEvent(xst, p->ev_hyb[ub], 0));
+        }
         {
-            ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
+            ProfSpan ps(p, xst, BFSM_KCLASS_PENCIL_GAIN);
             if (units) {
                 const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
                 const dim3 grid(PencilGeo<N>::WT / PR_WARPS, nu);
                 if (p->uniform_w)
-                    k_pencil_gain_reg<N, true, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
-                        p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
+                    k_pencil_gain_reg<N, true, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, xst>>>(
+                        hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
                 else
-                    k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
-                        p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
+                    k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, xst>>>(
+                        hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
+                if (split) CUDA_TRY(cudaEventRecord(p->ev_x[ub], xst));
             } else if (p->packed && p->one_slot_pencil)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
@@ -492,6 +574,8 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     }
     for (int ub = 0; ub < 2; ++ub)
         if (side && nyq_pending[ub]) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
+    if (p->split && p->xs && !p->profiling_serial && !p->fused)
+        for (int ub = 0; ub < std::min(2, ci); ++ub) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_x[ub], 0));
 
     // Qhat = sum_r coef_r(|l|^2) FFT3(S_r)   (cpp:249-273)
     {
@@ -524,6 +608,7 @@ template <int N> int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const
 
 template <int N> int launches_per_cell(const bfsm_plan *p)
 {
+    if (p->fused) return 2 + 1 + 1 + 1 + (p->n_r_local > 0 ? 1 : 0) + 1 + 2; // fwd, nyq extract, fused, nyq accum, accum, final
     const int chunks = (p->pairs_local + p->chunk - 1) / p->chunk;
     return 2 + (p->packed ? 1 + 3 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
 }
@@ -552,21 +637,21 @@ void lane_save(bfsm_plan *p, int k)
 {
     bfsm_plan::Lane &L = p->lanes[k];
     L.fhat = p->fhat; L.tmp = p->tmp; L.hyb = p->hyb; L.nyq = p->nyq; L.uvw = p->uvw;
-    L.qhat = p->qhat; L.S = p->S; L.side = p->side;
+    L.qhat = p->qhat; L.S = p->S; L.side = p->side; L.sync_flags = p->sync_flags;
     for (int j = 0; j < 2; ++j) { L.ev_plane[j] = p->ev_plane[j]; L.ev_nyq[j] = p->ev_nyq[j]; }
 }
 void lane_activate(bfsm_plan *p, int k)
 {
     const bfsm_plan::Lane &L = p->lanes[k];
     p->fhat = L.fhat; p->tmp = L.tmp; p->hyb = L.hyb; p->nyq = L.nyq; p->uvw = L.uvw;
-    p->qhat = L.qhat; p->S = L.S; p->side = L.side;
+    p->qhat = L.qhat; p->S = L.S; p->side = L.side; p->sync_flags = L.sync_flags;
     for (int j = 0; j < 2; ++j) { p->ev_plane[j] = L.ev_plane[j]; p->ev_nyq[j] = L.ev_nyq[j]; }
 }
 void lane_free(bfsm_plan *p, int k)
 {
     bfsm_plan::Lane &L = p->lanes[k];
     if (!L.allocated) return;
-    void *bufs[] = {L.fhat, L.tmp, L.hyb, L.nyq, L.uvw, L.qhat, L.S};
+    void *bufs[] = {L.fhat, L.tmp, L.hyb, L.nyq, L.uvw, L.qhat, L.S, L.sync_flags};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (L.side) cudaStreamDestroy(L.side);
@@ -641,14 +726,14 @@ int lane_alloc(bfsm_plan *p, int k)
     if ((rc = need((void **)&L.fhat, sizeof(cplx) * N3))) return give_up(rc);
     if ((rc = need((void **)&L.qhat, sizeof(cplx) * N3))) return give_up(rc);
     if ((rc = need((void **)&L.tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local)))) return give_up(rc);
-    if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk_capacity)))
+    if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * hyb_grids(p)))) return give_up(rc);
+    if (p->fused && (rc = need((void **)&L.sync_flags, sizeof(int) * 2 * (size_t)std::max(1, fused_subs(p)))))
         return give_up(rc);
     if ((rc = need((void **)&L.S, sizeof(double) * N3 * (size_t)std::max(1, p->S_slots_capacity) * nr)))
         return give_up(rc);
     if (p->packed) {
         if ((rc = need((void **)&L.nyq, sizeof(cplx) * 3 * N * N))) return give_up(rc);
-        if ((rc = need((void **)&L.uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk_capacity)))
-            return give_up(rc);
+        if ((rc = need((void **)&L.uvw, sizeof(cplx) * 3 * N * N * uvw_sets(p)))) return give_up(rc);
         if (p->use_side) {
             if (cudaStreamCreateWithFlags(&L.side, cudaStreamNonBlocking) != cudaSuccess)
                 return give_up(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
@@ -720,7 +805,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     }
     if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.nyq_groups < 0 || opt.gain_ctas < 0 ||
         opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 2 || opt.plane_kernel < 0 ||
-        opt.plane_kernel > 2)
+        opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
         return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
     if (!rho || !w_r || !sx || !sy || !sz || !w_s)
@@ -879,6 +964,33 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     p->uniform_w = 1;
     for (double w : rep_w)
         if (w != rep_w[0]) p->uniform_w = 0;
+    // fused persistent gain kernel: 64^3, packed mode, at least one pair, a GPU with room for every role
+    p->fused = (N == 64 && p->packed && opt.gain_pipeline == 2 && p->pairs_local > 0) ? 1 : 0;
+    if (opt.gain_pipeline == 2 && !p->fused && !(N == 64 && p->packed))
+        return (delete p, fail(BFSM_ERR_UNSUPPORTED, "gain_pipeline = 2 (fused kernel) needs a 64^3 grid in packed mode"));
+    p->split = (p->packed && opt.gain_pipeline == 3 && p->pairs_local > 0) ? 1 : 0;
+    if (p->split) {
+        p->split_ctas = opt.fused_pencil_ctas > 0 ? p->sm_count - opt.fused_pencil_ctas : (p->sm_count * 100) / 148;
+        p->split_ctas = std::max(1, std::min(p->sm_count, p->split_ctas));
+        p->pencil_kernel = 2; // the register-resident x stage is the one that is not LSU bound on few SMs
+    }
+    if (p->fused) {
+        p->fused_K = opt.fused_sub_pairs > 0 ? opt.fused_sub_pairs : 12;
+        p->fused_K = std::min(p->fused_K, p->pairs_local);
+        p->fused_D = opt.fused_ring > 0 ? opt.fused_ring : 2;
+        p->fused_NN = opt.fused_nyq_ctas > 0 ? opt.fused_nyq_ctas : 6;
+        p->fused_NQ = opt.fused_pencil_ctas > 0 ? opt.fused_pencil_ctas : (p->sm_count * 38) / 148;
+        if (p->fused_NN % 3 != 0 || p->fused_NQ < 1 || p->fused_NN + p->fused_NQ >= p->sm_count)
+            return (delete p, fail(BFSM_ERR_INVALID, "fused kernel: role sizes do not fit the device"));
+        p->chunk = p->chunk_capacity = std::max(1, p->pairs_local); // one launch covers the shard
+        if (opt.nyq_groups <= 0) {
+            // the Nyquist accumulate runs once over the whole shard: one pair group per radius if that
+            // keeps every group inside one radius (then all groups share one partial slot)
+            const int cand = std::min(32, std::max(4, p->n_r_local));
+            if (shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, cand))
+                p->GY = cand;
+        }
+    }
 
     int rc = BFSM_OK;
     auto bail = [&](int code) {
@@ -909,13 +1021,13 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bail(rc);
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
-    if ((rc = dev_alloc(p, (void **)&p->hyb,
-                        sizeof(cplx) * N3 * (p->packed ? 1 : 2) * (size_t)p->chunk)))
+    if ((rc = dev_alloc(p, (void **)&p->hyb, sizeof(cplx) * N3 * hyb_grids(p)))) return bail(rc);
+    if (p->fused &&
+        (rc = dev_alloc(p, (void **)&p->sync_flags, sizeof(int) * 2 * (size_t)std::max(1, fused_subs(p)))))
         return bail(rc);
     if (p->packed) {
         if ((rc = dev_alloc(p, (void **)&p->nyq, sizeof(cplx) * 3 * N * N))) return bail(rc);
-        if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 2 * 3 * N * N * (size_t)p->chunk)))
-            return bail(rc);
+        if ((rc = dev_alloc(p, (void **)&p->uvw, sizeof(cplx) * 3 * N * N * uvw_sets(p)))) return bail(rc);
         if (p->use_side) {
             if (cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess)
                 return bail(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
@@ -925,6 +1037,16 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
                     return bail(fail(BFSM_ERR_CUDA, "cudaEventCreate failed"));
             }
         }
+    }
+    if (p->split) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&p->xs, cudaStreamNonBlocking, prio_lo) != cudaSuccess)
+            return bail(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
+        for (int k = 0; k < 2; ++k)
+            if (cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&p->ev_hyb[k], cudaEventDisableTiming) != cudaSuccess)
+                return bail(fail(BFSM_ERR_CUDA, "cudaEventCreate failed"));
     }
     if ((rc = relayout(p))) return bail(rc); // unit table, slot layout, partial-sum slots S
     if ((rc = do_configure(p))) return bail(rc);
@@ -946,6 +1068,11 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
         if (p->ev_nyq[k]) cudaEventDestroy(p->ev_nyq[k]);
     }
     if (p->side) cudaStreamDestroy(p->side);
+    if (p->xs) cudaStreamDestroy(p->xs);
+    for (int k = 0; k < 2; ++k) {
+        if (p->ev_x[k]) cudaEventDestroy(p->ev_x[k]);
+        if (p->ev_hyb[k]) cudaEventDestroy(p->ev_hyb[k]);
+    }
     lanes_free(p);
     for (int k = 0; k < bfsm_plan::MAX_LANES; ++k) {
         if (p->lanes[k].main) cudaStreamDestroy(p->lanes[k].main);
@@ -969,22 +1096,21 @@ extern "C" int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, in
     if (n <= 0 || n_items <= 0 || n_ctas <= 0 || cta < 0 || cta >= n_ctas || capacity < 0 ||
         (capacity > 0 && (!planes || !items)))
         return -fail(BFSM_ERR_INVALID, "bfsm_debug_plane_work: bad argument");
-    const long long totA = (long long)n * n_items, totB = (long long)3 * n_items;
-    const int a_lo = (int)((totA * cta) / n_ctas), a_hi = (int)((totA * (cta + 1)) / n_ctas);
-    const int b_lo = (int)((totB * cta) / n_ctas), b_hi = (int)((totB * (cta + 1)) / n_ctas);
-    const int cntA = a_hi - a_lo, cnt = cntA + (b_hi - b_lo);
-    ItemWalk wk;
-    wk.n_items = n_items;
-    wk.iB = n + b_lo / n_items;
-    wk.itB = b_lo % n_items;
-    if (cntA > 0) { wk.i = a_lo / n_items; wk.it = a_lo % n_items; wk.leftA = cntA; }
-    else          { wk.i = wk.iB;          wk.it = wk.itB;         wk.leftA = -1; }
-    for (int k = 0; k < cnt && k < capacity; ++k) {
-        planes[k] = wk.i;
-        items[k] = wk.it;
-        wk.next();
-    }
-    return cnt;
+    // the very walker the pipelined kernel steps with (LaunchWalk<N>; its arithmetic does not depend on N
+    // beyond the plane count, k_plane_gain3 uses the same ranges)
+    auto run = [&](auto walk) {
+        walk.init(n_items, 0, cta, n_ctas);
+        for (int k = 0; k < walk.cnt && k < capacity; ++k) {
+            planes[k] = walk.i;
+            items[k] = walk.dst_item;
+            walk.next();
+        }
+        return walk.cnt;
+    };
+    if (n == 64) return run(LaunchWalk<64>());
+    if (n == 32) return run(LaunchWalk<32>());
+    if (n == 16) return run(LaunchWalk<16>());
+    return -fail(BFSM_ERR_UNSUPPORTED, "bfsm_debug_plane_work: n must be 16, 32 or 64");
 }
 
 extern "C" int bfsm_debug_shares_aligned(int pairs_local, int pair_lo, int n_dir, int chunk, int groups)
@@ -1031,6 +1157,7 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
     int dflt = (N == 64) ? Launch<64>::CHUNK : (N == 32) ? Launch<32>::CHUNK : Launch<16>::CHUNK;
     int c = chunk_pairs > 0 ? chunk_pairs : dflt;
     c = std::min(c, std::max(1, p->pairs_local));
+    if (p->fused) return BFSM_OK; // the fused kernel covers the shard in one launch; see fused_sub_pairs
     CUDA_TRY(cudaDeviceSynchronize());
     lanes_free(p); // re-allocated lazily with the new chunk size
     if (c > p->chunk_capacity) {
@@ -1075,6 +1202,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : 1;
     info->pencil_kernel = !p->packed ? 0 : p->pencil_kernel;
     info->batch_lanes_used = p->lanes_used_last;
+    info->gain_pipeline = p->fused ? 2 : (p->split ? 3 : 1);
     info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
 }
@@ -1116,6 +1244,7 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
         p->lanes_used_last = nl;
         CUDA_TRY(cudaEventRecord(p->ev_fork, st));
         for (int k = 0; k < nl; ++k) CUDA_TRY(cudaStreamWaitEvent(p->lanes[k].main, p->ev_fork, 0));
+        p->profiling_serial = true; // lanes run the unsplit pipeline (one hybrid buffer each)
         for (int c = 0; c < n_cells && !rc; ++c) {
             const int k = c % nl;
             lane_activate(p, k);
@@ -1124,6 +1253,7 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
             if (!rc) rc = do_finish(p, Q_dev + (size_t)c * N3, p->qhat, f_dev + (size_t)c * N3, ls);
         }
         lane_activate(p, 0);
+        p->profiling_serial = false;
         for (int k = 0; k < nl; ++k) {
             CUDA_TRY(cudaEventRecord(p->lanes[k].done, p->lanes[k].main));
             CUDA_TRY(cudaStreamWaitEvent(st, p->lanes[k].done, 0));

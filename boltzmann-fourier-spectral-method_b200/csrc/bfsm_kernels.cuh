@@ -377,41 +377,89 @@ struct ItemWalk {
 // register targets (setmaxnreg) of the three warpgroups; 384 threads launched at 168
 struct WsRegs { static constexpr int S1 = 240, S2 = 152, S3 = 112; };
 
-template <int N>
-__global__ void __launch_bounds__(3 * 128, 1)
-k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
-                const cplx *__restrict__ zpm, const cplx *__restrict__ twtab,
-                cplx *__restrict__ hyb, int pair0, int n_items,
-                const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
-                cplx *__restrict__ uvw)
+// Work list of one CTA of the stand-alone pipelined plane kernel: one launch = one "sub-chunk".
+// A walk names, for the current entry, the plane `i` (0..N-1 regular, N..N+2 Nyquist), the plan-local
+// pair `pair` (phase tables, weight), the destination slot `dst_item` (plane index into hyb: dst_item*N + i;
+// into uvw: dst_item*3 + i-N) and the sub-chunk `sub` it belongs to (hand-over granularity of the
+// fused kernel).
+template <int N> struct LaunchWalk {
+    ItemWalk w;
+    int cnt, pair0;
+    int i, pair, dst_item, sub;
+    __host__ __device__ __forceinline__ void init(int n_items, int pair0_, int cta, int n_ctas)
+    {
+        // an equal share of the N regular planes, then an equal share of the 3 costlier Nyquist planes
+        const long long totA = (long long)N * n_items, totB = (long long)3 * n_items;
+        const int a_lo = (int)((totA * cta) / n_ctas), a_hi = (int)((totA * (cta + 1)) / n_ctas);
+        const int b_lo = (int)((totB * cta) / n_ctas), b_hi = (int)((totB * (cta + 1)) / n_ctas);
+        const int cntA = a_hi - a_lo;
+        cnt = cntA + (b_hi - b_lo);
+        pair0 = pair0_;
+        w.n_items = n_items;
+        w.iB = N + b_lo / n_items;
+        w.itB = b_lo % n_items;
+        if (cntA > 0) { w.i = a_lo / n_items; w.it = a_lo % n_items; w.leftA = cntA; }
+        else          { w.i = w.iB;           w.it = w.itB;          w.leftA = -1; }
+        sub = 0;
+        load();
+    }
+    __host__ __device__ __forceinline__ void load() { i = w.i; pair = pair0 + w.it; dst_item = w.it; }
+    __host__ __device__ __forceinline__ void next() { w.next(); load(); }
+};
+
+// Hand-over of the fused kernel (plane role -> pencil role through an L2-resident ring of sub-chunks);
+// unused (null counters) by the stand-alone plane kernel.
+struct RingSync {
+    int *ready;          // [n_sub] plane CTAs that finished sub-chunk s
+    int *consumed;       // [n_sub] pairs x warp tiles of sub-chunk s the pencil role is done with
+    int n_sub, ring;     // sub-chunks in this launch, ring slots
+    int sub_pairs;       // pairs per sub-chunk (the last one may be shorter)
+    int n_pairs;         // pairs in this launch
+    int tiles;           // warp tiles per pair (expected consumed count = pairs of the sub-chunk x tiles)
+};
+
+__device__ __forceinline__ int ld_relaxed(const int *p)
 {
-    constexpr int R = N / 4, GT = 128, PITCH = N + 1, H = N / 2, NPL = N + 3, NBUF = 3;
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// The warp-specialised plane pipeline, shared by k_plane_gain_ws and by the plane role of
+// k_gain_fused.  Called by all 384 threads of a CTA; `walk0` is the CTA's work list.
+// SYNC: hand the sub-chunks over through `rs` (S3 waits for the ring slot before the first store of a
+// sub-chunk and publishes the sub-chunk after its last store -- also for sub-chunks in which this CTA
+// has no entry).
+// ---------------------------------------------------------------------------------------
+template <int N, bool SYNC, class Walk>
+__device__ __forceinline__ void
+plane_ws_pipeline(const Walk &walk0, unsigned char *smem_raw, const cplx *__restrict__ fhat,
+                  const cplx *__restrict__ phase, const cplx *__restrict__ zpm,
+                  const cplx *__restrict__ twtab, cplx *__restrict__ hyb,
+                  const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
+                  cplx *__restrict__ uvw, const RingSync &rs)
+{
+    constexpr int R = N / 4, GT = 128, PITCH = N + 1, H = N / 2, NBUF = 3;
     constexpr int T1 = GT;                // threads of stage S1
     constexpr int U1 = (4 * N) / T1;      // S1 units (row, residue) per thread and item
     constexpr int U = (4 * N) / GT;       // S2 / S3 units per thread and item
-    constexpr int BAR_FULL1 = 1, BAR_FULL2 = 4, BAR_EMPTY = 7, BAR_S1 = 10;
+    constexpr int BAR_FULL1 = 1, BAR_FULL2 = 4, BAR_EMPTY = 7, BAR_S1 = 10, BAR_S3 = 11;
     constexpr int REG_S1 = WsRegs::S1, REG_S2 = WsRegs::S2, REG_S3 = WsRegs::S3;
     static_assert(REG_S1 + REG_S2 + REG_S3 <= 3 * 168, "register targets exceed what the launch allocates");
-    static_assert(N == 64 && R == 16 && U == 2, "k_plane_gain_ws is written for N = 64");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    static_assert(N == 64 && R == 16 && U == 2, "the pipelined plane kernel is written for N = 64");
     cplx *bufs = reinterpret_cast<cplx *>(smem_raw);          // NBUF x (N x PITCH)
     cplx *phs = bufs + NBUF * N * PITCH;                      // 2 x 4N (S1's phase tables: ex, ey, ez, zpm)
     cplx *tws = phs + 2 * 4 * N;                              // N twiddles exp(+2 pi i t/N)
 
     const int wg = threadIdx.x / GT;
-
-    // this CTA's share of the flat work list (index = plane * n_items + item): an equal share of the
-    // N regular planes, then an equal share of the 3 costlier Nyquist planes (see k_plane_gain3)
-    const long long totA = (long long)N * n_items, totB = (long long)(NPL - N) * n_items;
-    const int a_lo = (int)((totA * blockIdx.x) / gridDim.x), a_hi = (int)((totA * (blockIdx.x + 1)) / gridDim.x);
-    const int b_lo = (int)((totB * blockIdx.x) / gridDim.x), b_hi = (int)((totB * (blockIdx.x + 1)) / gridDim.x);
-    const int cntA = a_hi - a_lo, cnt = cntA + (b_hi - b_lo);
-    ItemWalk walk0;
-    walk0.n_items = n_items;
-    walk0.iB = N + b_lo / n_items;
-    walk0.itB = b_lo % n_items;
-    if (cntA > 0) { walk0.i = a_lo / n_items; walk0.it = a_lo % n_items; walk0.leftA = cntA; }
-    else          { walk0.i = walk0.iB;       walk0.it = walk0.itB;      walk0.leftA = -1; }
+    const int cnt = walk0.cnt;
 
     if (threadIdx.x < N) tws[threadIdx.x] = __ldg(&twtab[threadIdx.x]);
     __syncthreads();
@@ -424,24 +472,24 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         cplx fr[U1][R];                        // fr[u][a] = plane[j][4a + b_u]
         int cur_plane = -1;
         // the phase table of item n+1 is copied (cp.async) into the other slot while item n is computed
-        auto stage_phase = [&](int it_src, int slot_dst) {
-            const cplx *src = phase + (size_t)(pair0 + it_src) * 3 * N;
+        auto stage_phase = [&](int pair_src, int slot_dst) {
+            const cplx *src = phase + (size_t)pair_src * 3 * N;
             cplx *dstp = phs + slot_dst * 4 * N;
             if (ts < 3 * N) cp_async16(dstp + ts, src + ts);
             if (ts + GT < 3 * N) cp_async16(dstp + ts + GT, src + ts + GT);
             // fourth row: (Re+Im, Re-Im) of the z phase, taken by the last N threads
-            if (ts >= T1 - N) cp_async16(dstp + 3 * N + (ts - (T1 - N)), zpm + (size_t)(pair0 + it_src) * N + (ts - (T1 - N)));
+            if (ts >= T1 - N) cp_async16(dstp + 3 * N + (ts - (T1 - N)), zpm + (size_t)pair_src * N + (ts - (T1 - N)));
         };
-        ItemWalk wk = walk0;                   // plane and item of the current list entry
-        if (cnt > 0) stage_phase(wk.it, 0);
+        Walk wk = walk0;                       // plane and item of the current list entry
+        if (cnt > 0) stage_phase(wk.pair, 0);
         cp_async_commit();
         cp_async_wait<0>();
         bar_sync_n(BAR_S1, T1);
         int buf_id = 0, slot = 0;
         for (int n = 0; n < cnt; ++n) {
-            const int i = wk.i, it = wk.it;
+            const int i = wk.i, pair = wk.pair;
             wk.next();                         // next entry: its phase table goes to the other slot
-            if (n + 1 < cnt) stage_phase(wk.it, slot ^ 1);
+            if (n + 1 < cnt) stage_phase(wk.pair, slot ^ 1);
             cp_async_commit();
             cplx *buf = bufs + buf_id * N * PITCH;
             if (n >= NBUF) bar_sync_n(BAR_EMPTY + buf_id, T1 + GT); // S3 is done with item n - NBUF
@@ -494,7 +542,7 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 const int nq = i - N;
                 const int axA = (nq == 0) ? 1 : 0, axB = (nq == 2) ? 1 : 2;
                 const cplx efix = P[nq * N + H];
-                const double sw = 0.5 * sqrt(__ldg(&pair_w[pair0 + it]));
+                const double sw = 0.5 * sqrt(__ldg(&pair_w[pair]));
                 const cplx ea = P[axA * N + j];
                 const cplx eat = (j == H) ? ea : make_double2(ea.x, -ea.y);
                 const cplx fa = cmul(efix, ea), fat = cmul(efix, eat);
@@ -581,11 +629,37 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         // unit q = t + 128 u: column slot q % N = t % N, k1' = q / N = t / N + 2 u
         const int s3slot = t % N;
         int buf_id = 0;
-        ItemWalk wk = walk0;
+        Walk wk = walk0;
+        // fused hand-over: sub-chunks [0, published) have been published by this CTA; `cur_sub` is the
+        // sub-chunk whose ring slot this CTA may write
+        int published = 0, cur_sub = -1;
+        auto publish_upto = [&](int s_end) { // all stores of sub-chunks < s_end are issued
+            if (published < s_end) {
+                __threadfence();
+                bar_sync_n(BAR_S3, GT);
+                if (t == 0)
+                    for (int s = published; s < s_end; ++s) atomicAdd(rs.ready + s, 1);
+                published = s_end;
+            }
+        };
         for (int n = 0; n < cnt; ++n) {
             const cplx *buf = bufs + buf_id * N * PITCH;
-            cplx *dst = (wk.i < N) ? hyb + ((size_t)wk.it * N + wk.i) * N * N
-                                   : uvw + ((size_t)wk.it * 3 + (wk.i - N)) * N * N;
+            if (SYNC && wk.sub != cur_sub) {
+                publish_upto(wk.sub);
+                cur_sub = wk.sub;
+                if (cur_sub >= rs.ring) {
+                    // the ring slot still holds sub-chunk cur_sub - ring: wait until it has been read
+                    const int old = cur_sub - rs.ring;
+                    const int old_pairs = min(rs.sub_pairs, rs.n_pairs - old * rs.sub_pairs);
+                    if (t == 0) {
+                        while (ld_relaxed(rs.consumed + old) < old_pairs * rs.tiles) __nanosleep(100);
+                        __threadfence();
+                    }
+                    bar_sync_n(BAR_S3, GT);
+                }
+            }
+            cplx *dst = (wk.i < N) ? hyb + ((size_t)wk.dst_item * N + wk.i) * N * N
+                                   : uvw + ((size_t)wk.dst_item * 3 + (wk.i - N)) * N * N;
             wk.next();
             bar_sync_n(BAR_FULL2 + buf_id, 2 * GT);
 #pragma unroll
@@ -602,7 +676,23 @@ k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             bar_arrive_n(BAR_EMPTY + buf_id, T1 + GT); // after the stores that consumed the loads
             buf_id = (buf_id + 1 == NBUF) ? 0 : buf_id + 1;
         }
+        if (SYNC) publish_upto(rs.n_sub);
     }
+}
+
+template <int N>
+__global__ void __launch_bounds__(3 * 128, 1)
+k_plane_gain_ws(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
+                const cplx *__restrict__ zpm, const cplx *__restrict__ twtab,
+                cplx *__restrict__ hyb, int pair0, int n_items,
+                const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
+                cplx *__restrict__ uvw)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LaunchWalk<N> walk;
+    walk.init(n_items, pair0, blockIdx.x, gridDim.x);
+    RingSync none = {};
+    plane_ws_pipeline<N, false>(walk, smem_raw, fhat, phase, zpm, twtab, hyb, nyq, pair_w, uvw, none);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -63,18 +63,23 @@ template <int N> __device__ __forceinline__ int pencil_out_x(int j, int c, int d
     return 8 * c + 4 * d + (j >> 2) + 16 * ((j >> 1) & 1) + 32 * (j & 1);
 }
 
-// One pair of one warp tile: load, transform, accumulate.  `src` points at this lane's first entry
-// (i = its sub-sequence index) of the pair's hybrid grid; c, d are the lane's sub-sequence bits
-// (i = LANES a + 2 c + d for N = 64, 2 a + c for N = 32), tw[m] = W_64^(8c + 4d + m) (N = 64 only).
-template <int N, bool UNIFORM_W>
-__device__ __forceinline__ void pencil_reg_pair(const cplx *__restrict__ src, int c, int d,
-                                                const cplx (&tw)[4], double w, double (&acc)[16])
+// Loads this lane's 16 entries of one pair: `src` points at its first entry (i = its sub-sequence
+// index) of the pair's hybrid grid.
+template <int N> __device__ __forceinline__ void pencil_reg_load(const cplx *__restrict__ src, cplx (&v)[16])
 {
     constexpr int LANES = PencilGeo<N>::LANES;
     constexpr size_t N2 = (size_t)N * N;
-    cplx v[16];
 #pragma unroll
     for (int a = 0; a < 16; ++a) v[a] = ld_cg(src + (size_t)(LANES * a) * N2);
+}
+
+// Transforms the 16 loaded entries and accumulates.  c, d are the lane's sub-sequence bits
+// (i = LANES a + 2 c + d for N = 64, 2 a + c for N = 32), tw[m] = W_64^(8c + 4d + m) (N = 64 only).
+template <int N, bool UNIFORM_W>
+__device__ __forceinline__ void pencil_reg_compute(cplx (&v)[16], int c, int d, const cplx (&tw)[4],
+                                                   double w, double (&acc)[16])
+{
+    constexpr int LANES = PencilGeo<N>::LANES;
     Dft<16, +1>::run(v);
     auto add = [&](int j, cplx o) {
         if (UNIFORM_W) {
@@ -84,34 +89,44 @@ __device__ __forceinline__ void pencil_reg_pair(const cplx *__restrict__ src, in
             acc[j] = fma(w, o.x * o.x - o.y * o.y, acc[j]);
         }
     };
+    // step over c (couple = lanes 8*(LANES/2) apart): lane c finishes k1 in [8c, 8c + 8):
+    // Z[8c + m], Z[8c + m + 16] = Y_0[k1] +- W_32^k1 Y_1[k1],  W_32^(8c + m) = i^c W_32^m
+    auto step_c = [&](int m, cplx &zlo, cplx &zhi) {
+        const cplx lo = v[dft16_reg(m)], hi = v[dft16_reg(8 + m)];
+        const cplx keep = c ? hi : lo;
+        const cplx recv = shfl_xor_c(c ? lo : hi, LANES == 4 ? 8 : 16);
+        const cplx y0 = c ? recv : keep, y1 = c ? keep : recv;
+        cplx t = cmul(y1, w64<+1>(2 * m));
+        if (c) t = mul_i(t);
+        zlo = cadd(y0, t);
+        zhi = csub(y0, t);
+    };
     if constexpr (LANES == 1) {
 #pragma unroll
         for (int k = 0; k < 16; ++k) add(k, v[dft16_reg(k)]);
-    } else {
-        // step over c (couple = lanes 8*(LANES/2) apart): lane c finishes k1 in [8c, 8c + 8),
-        // z[2m], z[2m+1] = Z[8c + m], Z[8c + m + 16];  W_32^(8c + m) = i^c W_32^m
-        cplx z[16];
+    } else if constexpr (LANES == 2) {
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            const cplx lo = v[dft16_reg(m)], hi = v[dft16_reg(8 + m)];
-            const cplx keep = c ? hi : lo;
-            const cplx recv = shfl_xor_c(c ? lo : hi, LANES == 4 ? 8 : 16);
-            const cplx y0 = c ? recv : keep, y1 = c ? keep : recv;
-            cplx t = cmul(y1, w64<+1>(2 * m));
-            if (c) t = mul_i(t);
-            z[2 * m] = cadd(y0, t);
-            z[2 * m + 1] = csub(y0, t);
+            cplx zlo, zhi;
+            step_c(m, zlo, zhi);
+            add(2 * m, zlo);
+            add(2 * m + 1, zhi);
         }
-        if constexpr (LANES == 2) {
+    } else {
+        // step over d (couple = lanes 16 apart): with z[j] = Z_d[k(j)], k(j) = 8c + (j>>1) + 16 (j&1)
+        // (z[2m], z[2m+1] come from step_c(m)), lane d finishes j in [8d, 8d + 8):
+        //   k = 8c + 4d + (jj>>1) + 16 (jj&1),  W_64^k = i^(jj&1) tw[jj>>1];  acc[2jj], acc[2jj+1] <- X[k], X[k+32]
+        // Interleaved so that only four z values are alive at a time: jj = 2mm, 2mm+1 need z[2mm],
+        // z[2mm+1] (step_c(mm)) and z[8+2mm], z[8+2mm+1] (step_c(4+mm)).
 #pragma unroll
-            for (int j = 0; j < 16; ++j) add(j, z[j]);
-        } else {
-            // step over d (couple = lanes 16 apart): both hold Z_d[k] for k = 8c + (j>>1) + 16 (j&1);
-            // lane d finishes j in [8d, 8d + 8):  k = 8c + 4d + (jj>>1) + 16 (jj&1),
-            // W_64^k = i^(jj&1) tw[jj>>1];  acc[2jj], acc[2jj+1] <- X[k], X[k + 32]
+        for (int mm = 0; mm < 4; ++mm) {
+            cplx zl[2], zh[2];
+            step_c(mm, zl[0], zl[1]);
+            step_c(4 + mm, zh[0], zh[1]);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                const cplx lo = z[jj], hi = z[8 + jj];
+            for (int e = 0; e < 2; ++e) {
+                const int jj = 2 * mm + e;
+                const cplx lo = zl[e], hi = zh[e];
                 const cplx keep = d ? hi : lo;
                 const cplx recv = shfl_xor_c(d ? lo : hi, 16);
                 const cplx y0 = d ? recv : keep, y1 = d ? keep : recv;
@@ -122,6 +137,16 @@ __device__ __forceinline__ void pencil_reg_pair(const cplx *__restrict__ src, in
             }
         }
     }
+}
+
+// One pair of one warp tile: load, transform, accumulate.
+template <int N, bool UNIFORM_W>
+__device__ __forceinline__ void pencil_reg_pair(const cplx *__restrict__ src, int c, int d,
+                                                const cplx (&tw)[4], double w, double (&acc)[16])
+{
+    cplx v[16];
+    pencil_reg_load<N>(src, v);
+    pencil_reg_compute<N, UNIFORM_W>(v, c, d, tw, w, acc);
 }
 
 // Lane geometry shared by the stand-alone kernel and the fused kernel's pencil role.

@@ -89,7 +89,16 @@ typedef struct {
     int side_stream;       /* 1: Nyquist accumulate on an internal side stream (default), 0: in line */
     int batch_lanes;       /* cells kept in flight by bfsm_collide(n_cells > 1): 1..4, 0 = default (4) */
     int gain_ctas;         /* persistent CTAs of k_plane_gain3; 0 = SMs x occupancy */
-    int reserved[7];
+    int gain_pipeline;     /* 0 = default, 1 = one plane + one x kernel per chunk (hybrid grids through
+                              HBM), 2 = fused persistent kernel (64^3 packed mode only): plane, Nyquist and
+                              x roles on disjoint SMs, hybrid grids through an L2-resident ring, 3 = split:
+                              the plane kernel of chunk c+1 and the x stage of chunk c run side by side on
+                              two streams and disjoint SMs (two hybrid scratch buffers, through HBM) */
+    int fused_sub_pairs;   /* fused kernel: pairs per hand-over (sub-chunk); 0 = default */
+    int fused_ring;        /* fused kernel: ring slots (sub-chunks in flight); 0 = default (2) */
+    int fused_pencil_ctas; /* fused / split pipeline: SMs left to the x stage; 0 = default */
+    int fused_nyq_ctas;    /* fused kernel: CTAs of the Nyquist-plane role, a multiple of 3; 0 = default */
+    int reserved[2];
 } bfsm_plan_options;
 
 void bfsm_plan_options_init(bfsm_plan_options *opts);
@@ -158,6 +167,7 @@ typedef struct {
     int pencil_kernel;       /* x stage in use: 0 k_pencil_gain (unpacked mode), 1 k_pencil_gain_async
                                 (cp.async ring), 2 k_pencil_gain_reg (register resident) */
     int batch_lanes_used;    /* lanes the last bfsm_collide(n_cells > 1) ran on (1 before any) */
+    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel, 3 = split */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);

@@ -166,6 +166,23 @@ __global__ void __launch_bounds__(256) k_split(double2 *wr, const double2 *rd, s
     }
 }
 
+// MLP-rich read: 8 independent 16-byte loads per thread and iteration (per-SM L2 read bandwidth probe)
+__global__ void __launch_bounds__(1024) k_read8(const double2 *p, size_t n, double *out)
+{
+    double s = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 7 * stride < n; i += 8 * stride) {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v[k].x), "=d"(v[k].y) : "l"(p + i + k * stride));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += v[k].x + v[k].y;
+    }
+    if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <class F> float time_ms(F f, int reps)
 {
     cudaEvent_t a, b;
@@ -260,6 +277,21 @@ int main()
                    "\"split_write_plus_read_GBs\": %.0f}\n",
                    mib, (double)(mib << 20) / (tw * 1e-3) / 1e9, (double)(mib << 20) / (tr * 1e-3) / 1e9,
                    2.0 * (double)(mib << 20) / (ts * 1e-3) / 1e9);
+        }
+    }
+    // ---- per-SM L2 read bandwidth: n_sm CTAs of 1024 threads (one per SM) stream an L2-resident 48 MiB
+    {
+        double2 *buf;
+        const size_t bytes = (size_t)48 << 20, n = bytes / sizeof(double2);
+        CK(cudaMalloc(&buf, bytes));
+        CK(cudaMemset(buf, 0, bytes));
+        const int counts[] = {8, 19, 38, 50, 74, 110, 148, 296};
+        for (int c : counts) {
+            // warm L2, then time
+            k_read8<<<c, 1024>>>(buf, n, out);
+            float t = time_ms([&] { k_read8<<<c, 1024>>>(buf, n, out); }, 10);
+            printf("{\"probe\": \"l2_read_per_sm\", \"ctas_1024thr\": %d, \"total_GBs\": %.0f, \"per_cta_GBs\": %.1f}\n", c,
+                   (double)bytes / (t * 1e-3) / 1e9, (double)bytes / (t * 1e-3) / 1e9 / c);
         }
     }
     return 0;
