@@ -41,11 +41,11 @@ class PlanOptions(ctypes.Structure):
     after bfsm_plan_options_init."""
     _fields_ = [
         ("struct_size", ctypes.c_int), ("chunk_pairs", ctypes.c_int), ("pencil_kernel", ctypes.c_int),
-        ("seg_pairs", ctypes.c_int), ("plane_kernel", ctypes.c_int), ("nyq_groups", ctypes.c_int),
+        ("seg_pairs", ctypes.c_int), ("plane_kernel", ctypes.c_int),
         ("side_stream", ctypes.c_int), ("batch_lanes", ctypes.c_int), ("gain_ctas", ctypes.c_int),
         ("gain_pipeline", ctypes.c_int), ("fused_sub_pairs", ctypes.c_int), ("fused_ring", ctypes.c_int),
         ("fused_pencil_ctas", ctypes.c_int), ("fused_nyq_ctas", ctypes.c_int),
-        ("reserved", ctypes.c_int * 2),
+        ("reserved", ctypes.c_int * 3),
     ]
 
 
@@ -55,7 +55,7 @@ class PlanOptions(ctypes.Structure):
 ENV_OPTIONS = {
     "BFSM_CHUNK_PAIRS": "chunk_pairs", "BFSM_PENCIL_KERNEL": "pencil_kernel",
     "BFSM_SEG_PAIRS": "seg_pairs", "BFSM_PLANE_KERNEL": "plane_kernel",
-    "BFSM_NYQ_GROUPS": "nyq_groups", "BFSM_SIDE_STREAM": "side_stream",
+    "BFSM_SIDE_STREAM": "side_stream",
     "BFSM_BATCH_LANES": "batch_lanes", "BFSM_GAIN_CTAS": "gain_ctas",
     "BFSM_GAIN_PIPELINE": "gain_pipeline", "BFSM_FUSED_SUB_PAIRS": "fused_sub_pairs",
     "BFSM_FUSED_RING": "fused_ring", "BFSM_FUSED_PENCIL_CTAS": "fused_pencil_ctas",

@@ -53,14 +53,13 @@ struct bfsm_plan {
     double gamma = 0, b_gamma = 0, L = 0;
     int folded = 0;
     int packed = 1;   // Hermitian packing: one 3-D transform per pair + Nyquist-plane correction
-    int GY = 4;       // pair groups (= S partial slots) of k_nyq_accum
     int pencil_kernel = 2; // x stage (packed): 1 = staged cp.async ring, 2 = register resident (units)
     int plane_ws = 0;      // warp-specialised pipelined plane kernel (packed mode, N = 64)
     int use_side = 1;      // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
     // Staged x stage and Nyquist accumulate: CTA row gy owns share gy of a chunk's pairs and, in general,
     // partial slot gy of S.  When every share of every launch starts at a radius boundary no two rows
     // touch the same (radius, tile), so one slot per kernel is enough (decided by update_slot_layout).
-    int one_slot_pencil = 0, one_slot_nyq = 0;
+    int one_slot_pencil = 0;
     // Register-resident x stage: the pair list is cut into work units (<= seg_pairs pairs of one radius
     // inside one launch); unit k of a radius owns partial slot k of S, written once with plain stores.
     int seg_pairs = 0, unit_slots = 0, uniform_w = 0;
@@ -72,11 +71,7 @@ struct bfsm_plan {
     // fused persistent gain kernel (64^3 packed mode): roles, sub-chunk size, ring depth
     int fused = 0, fused_K = 0, fused_D = 0, fused_NQ = 0, fused_NN = 0;
     int *sync_flags = nullptr;    // [2 * n_sub] ready / consumed counters of the fused kernel
-    // split pipeline: the plane kernel of chunk c+1 (on split_ctas SMs) runs next to the x stage of
-    // chunk c (second stream, the remaining SMs); two hybrid scratch buffers
-    int split = 0, split_ctas = 0;
-    cudaStream_t xs = nullptr;
-    cudaEvent_t ev_x[2] = {nullptr, nullptr}, ev_hyb[2] = {nullptr, nullptr};
+
     int S_slots_capacity = 0;     // partial slots S was allocated for
     int chunk_capacity = 0;       // pairs the per-chunk scratch (hyb, uvw) was allocated for
     bfsm_plan_options opt;
@@ -106,7 +101,7 @@ struct bfsm_plan {
     cplx *fhat = nullptr;  // [N^3]
     cplx *tmp = nullptr;   // [max(2, n_r_local)][N^3]  hybrid scratch of the single-shot stages
     cplx *hyb = nullptr;   // [(packed ? 1 : 2)*chunk][N^3]
-    double *S = nullptr;   // [G (+GY when packed)][n_r_local][N^3]
+    double *S = nullptr;   // [x-stage slots + Nyquist slots][n_r_local][N^3]
     cplx *nyq = nullptr;   // [3][N][N] Nyquist planes of fhat (packed mode)
     cplx *uvw = nullptr;   // [2][chunk][3][N][N] (packed mode, double buffered)
     cplx *qhat = nullptr;  // [N^3]
@@ -137,7 +132,6 @@ struct bfsm_plan {
 
     // optional per-kernel-class timing (bfsm_collide_profiled)
     bool profiling = false, profile_failed = false;
-    bool profiling_serial = false; // batch lanes: scratch of lanes >= 1 has no second hybrid buffer
     struct Span { int cls; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::vector<cudaEvent_t> event_pool;
@@ -345,14 +339,14 @@ void update_slot_layout(bfsm_plan *p)
         return shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, groups);
     };
     p->one_slot_pencil = (staged && p->G > 1 && aligned(p->G)) ? 1 : 0;
-    p->one_slot_nyq = (p->packed && p->GY > 1 && aligned(p->GY)) ? 1 : 0;
 }
 bool pencil_units_active(const bfsm_plan *p) { return p->packed && (p->pencil_kernel == 2 || p->fused); }
+bool units_needed(const bfsm_plan *p) { return p->packed != 0; } // the Nyquist accumulate always walks units
 // hybrid grids / Nyquist-field sets the per-launch scratch holds
 size_t hyb_grids(const bfsm_plan *p)
 {
     if (p->fused) return (size_t)p->fused_D * p->fused_K;
-    return (size_t)(p->packed ? 1 : 2) * p->chunk_capacity * (p->split ? 2 : 1);
+    return (size_t)(p->packed ? 1 : 2) * p->chunk_capacity;
 }
 size_t uvw_sets(const bfsm_plan *p) { return p->fused ? (size_t)std::max(1, p->pairs_local) : (size_t)2 * p->chunk_capacity; }
 int fused_subs(const bfsm_plan *p) { return (p->pairs_local + p->fused_K - 1) / std::max(1, p->fused_K); }
@@ -361,13 +355,13 @@ int pencil_slots(const bfsm_plan *p)
     if (pencil_units_active(p)) return p->unit_slots;
     return p->one_slot_pencil ? 1 : p->G;
 }
-int nyq_slots(const bfsm_plan *p) { return !p->packed ? 0 : (p->one_slot_nyq ? 1 : p->GY); }
+int nyq_slots(const bfsm_plan *p) { return p->packed ? p->unit_slots : 0; } // one per work unit of a radius
 
 // (re)builds everything that depends on the chunk size: unit table, slot layout, S capacity
 int relayout(bfsm_plan *p)
 {
     const size_t N3 = (size_t)p->N * p->N * p->N;
-    if (pencil_units_active(p)) {
+    if (units_needed(p)) {
         std::vector<int> slots_of_r;
         p->unit_slots = build_units(p, slots_of_r);
         if (p->units) { cudaFree(p->units); p->units = nullptr; }
@@ -426,12 +420,8 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     const bool units = pencil_units_active(p);
     const int pslots = pencil_slots(p), nslots = nyq_slots(p);
     const size_t slot_stride = (size_t)p->n_r_local * N3;
-    double *S2 = p->S + (size_t)pslots * slot_stride; // Nyquist slots
-    if (units) {
-        if (nslots) CUDA_TRY(cudaMemsetAsync(S2, 0, sizeof(double) * (size_t)nslots * slot_stride, st));
-    } else {
-        CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)(pslots + nslots) * slot_stride, st));
-    }
+    double *S2 = p->S + (size_t)pslots * slot_stride; // Nyquist slots (written once per unit, never cleared)
+    if (!units) CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)pslots * slot_stride, st));
     if (p->packed) {
         ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
         k_extract_nyq<N><<<(3 * N * N + 255) / 256, 256, 0, st>>>(p->fhat, p->nyq);
@@ -469,14 +459,9 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             }
             {
                 ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
-                const int GY = std::min(p->GY, p->pairs_local);
                 constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
-                if (p->one_slot_nyq)
-                    k_nyq_accum<N, true><<<dim3(NYQ_TILES, GY), 256, 0, st>>>(
-                        p->uvw, p->pair_r, p->r_end, S2, 0, p->pairs_local, p->n_r_local);
-                else
-                    k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, st>>>(
-                        p->uvw, p->pair_r, p->r_end, S2, 0, p->pairs_local, p->n_r_local);
+                k_nyq_accum<N><<<dim3(NYQ_TILES, (int)p->h_units.size()), 256, 0, st>>>(
+                    p->uvw, 0, p->units, S2, p->n_r_local);
             }
         }
     }
@@ -488,10 +473,6 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         const int items = p->packed ? nc : 2 * nc;
         const int ub = ci & 1; // uvw buffer of this chunk
         cplx *uvw = p->packed ? p->uvw + (size_t)ub * 3 * N * N * p->chunk_capacity : nullptr;
-        // split pipeline: chunk ci uses hybrid buffer ci & 1, free once the x stage of chunk ci-2 is done
-        const bool split = p->split && p->xs && !p->profiling_serial;
-        cplx *hyb = p->hyb + (split ? (size_t)ub * N3 * p->chunk_capacity : 0);
-        if (split && ci >= 2) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_x[ub], 0));
         if (side && nyq_pending[ub]) { // k_nyq_accum of chunk ci-2 must be done with uvw[ub]
             CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
             nyq_pending[ub] = false;
@@ -502,14 +483,14 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
             if (N == 64 && p->packed && p->plane_ws) {
                 if constexpr (N == 64) {
-                    const int grid = std::min(split ? p->split_ctas : p->sm_count, (N + 3) * items);
+                    const int grid = std::min(p->sm_count, (N + 3) * items);
                     k_plane_gain_ws<N><<<grid, 384, plane_ws_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->zpm, p->tw, hyb, c0, items, p->nyq, p->pair_w, uvw);
+                        p->fhat, p->phase, p->zpm, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
                 }
             } else if (p->packed)
                 k_plane_gain3<N, Lc::GROUPS, Lc::MINB>
                     <<<ctas, 4 * N * Lc::GROUPS, plane_gain3_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, hyb, c0, items, p->nyq, p->pair_w, uvw);
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
             else
                 k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
                     <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
@@ -525,14 +506,9 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             }
             {
                 ProfSpan ps(p, ns, BFSM_KCLASS_NYQUIST);
-                const int GY = std::min(p->GY, nc);
                 constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
-                if (p->one_slot_nyq)
-                    k_nyq_accum<N, true><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
-                        uvw, p->pair_r, p->r_end, S2, c0, nc, p->n_r_local);
-                else
-                    k_nyq_accum<N><<<dim3(NYQ_TILES, GY), 256, 0, ns>>>(
-                        uvw, p->pair_r, p->r_end, S2, c0, nc, p->n_r_local);
+                const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
+                k_nyq_accum<N><<<dim3(NYQ_TILES, nu), 256, 0, ns>>>(uvw, c0, p->units + u0, S2, p->n_r_local);
             }
             if (side) {
                 CUDA_TRY(cudaEventRecord(p->ev_nyq[ub], ns));
@@ -540,24 +516,17 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             }
         }
         const int G = std::min(p->G, nc);
-        // split pipeline: the x stage of this chunk goes to the second stream, behind the plane kernel
-        cudaStream_t xst = split ? p->xs : st;
-        if (split) {
-            CUDA_TRY(cudaEventRecord(p->ev_hyb[ub], st));
-            CUDA_TRY(cudaStreamWaitEvent(xst, p->ev_hyb[ub], 0));
-        }
         {
-            ProfSpan ps(p, xst, BFSM_KCLASS_PENCIL_GAIN);
+            ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
             if (units) {
                 const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
                 const dim3 grid(PencilGeo<N>::WT / PR_WARPS, nu);
                 if (p->uniform_w)
-                    k_pencil_gain_reg<N, true, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, xst>>>(
-                        hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
+                    k_pencil_gain_reg<N, true, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
+                        p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
                 else
-                    k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, xst>>>(
-                        hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
-                if (split) CUDA_TRY(cudaEventRecord(p->ev_x[ub], xst));
+                    k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
+                        p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
             } else if (p->packed && p->one_slot_pencil)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
@@ -574,8 +543,6 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     }
     for (int ub = 0; ub < 2; ++ub)
         if (side && nyq_pending[ub]) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_nyq[ub], 0));
-    if (p->split && p->xs && !p->profiling_serial && !p->fused)
-        for (int ub = 0; ub < std::min(2, ci); ++ub) CUDA_TRY(cudaStreamWaitEvent(st, p->ev_x[ub], 0));
 
     // Qhat = sum_r coef_r(|l|^2) FFT3(S_r)   (cpp:249-273)
     {
@@ -583,7 +550,7 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         if (p->n_r_local > 0) {
             k_plane<N, -1, PLANE_REAL><<<dim3(N, p->n_r_local), N * Geo<N>::B, plane_smem<N>(), st>>>(
                 p->S, pslots, slot_stride, nullptr, nullptr, nullptr, p->tw, p->tmp,
-                units ? p->slots_of_r : nullptr, S2, nslots);
+                units ? p->slots_of_r : nullptr, S2, nslots, p->packed ? p->slots_of_r : nullptr);
         }
         k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
     }
@@ -803,9 +770,9 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
             return fail(BFSM_ERR_INVALID, "bfsm_plan_options: struct_size mismatch (call bfsm_plan_options_init)");
         opt = *opts;
     }
-    if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.nyq_groups < 0 || opt.gain_ctas < 0 ||
+    if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.gain_ctas < 0 ||
         opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 2 || opt.plane_kernel < 0 ||
-        opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
+        opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 2)
         return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
     if (!rho || !w_r || !sx || !sy || !sz || !w_s)
@@ -954,8 +921,9 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
         const int occ = (N == 64) ? 1 : (N == 32) ? 2 : 4;
         p->gy = opt.gain_ctas > 0 ? opt.gain_ctas : p->sm_count * occ;
     }
-    p->GY = opt.nyq_groups > 0 ? opt.nyq_groups : (N == 64 ? 4 : (N == 32 ? 8 : 16));
-    p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : 2;
+    // x stage: at 64^3 both kernels are HBM bound and the staged one interferes less with the side-stream
+    // Nyquist accumulate (173 vs 170 evals/s); at 32^3 / 16^3 the register-resident one is 15 % faster
+    p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : (N == 64 ? 1 : 2);
     p->plane_ws = (N == 64 && opt.plane_kernel != 1) ? 1 : 0;
     // work units of the register-resident x stage: a quarter of a radius' directions, at most 24 pairs
     p->seg_pairs = opt.seg_pairs > 0 ? opt.seg_pairs : std::max(1, std::min(24, (n_dir + 3) / 4));
@@ -968,12 +936,6 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     p->fused = (N == 64 && p->packed && opt.gain_pipeline == 2 && p->pairs_local > 0) ? 1 : 0;
     if (opt.gain_pipeline == 2 && !p->fused && !(N == 64 && p->packed))
         return (delete p, fail(BFSM_ERR_UNSUPPORTED, "gain_pipeline = 2 (fused kernel) needs a 64^3 grid in packed mode"));
-    p->split = (p->packed && opt.gain_pipeline == 3 && p->pairs_local > 0) ? 1 : 0;
-    if (p->split) {
-        p->split_ctas = opt.fused_pencil_ctas > 0 ? p->sm_count - opt.fused_pencil_ctas : (p->sm_count * 100) / 148;
-        p->split_ctas = std::max(1, std::min(p->sm_count, p->split_ctas));
-        p->pencil_kernel = 2; // the register-resident x stage is the one that is not LSU bound on few SMs
-    }
     if (p->fused) {
         p->fused_K = opt.fused_sub_pairs > 0 ? opt.fused_sub_pairs : 12;
         p->fused_K = std::min(p->fused_K, p->pairs_local);
@@ -983,13 +945,6 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
         if (p->fused_NN % 3 != 0 || p->fused_NQ < 1 || p->fused_NN + p->fused_NQ >= p->sm_count)
             return (delete p, fail(BFSM_ERR_INVALID, "fused kernel: role sizes do not fit the device"));
         p->chunk = p->chunk_capacity = std::max(1, p->pairs_local); // one launch covers the shard
-        if (opt.nyq_groups <= 0) {
-            // the Nyquist accumulate runs once over the whole shard: one pair group per radius if that
-            // keeps every group inside one radius (then all groups share one partial slot)
-            const int cand = std::min(32, std::max(4, p->n_r_local));
-            if (shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, cand))
-                p->GY = cand;
-        }
     }
 
     int rc = BFSM_OK;
@@ -1038,16 +993,6 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
             }
         }
     }
-    if (p->split) {
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if (cudaStreamCreateWithPriority(&p->xs, cudaStreamNonBlocking, prio_lo) != cudaSuccess)
-            return bail(fail(BFSM_ERR_CUDA, "cudaStreamCreate failed"));
-        for (int k = 0; k < 2; ++k)
-            if (cudaEventCreateWithFlags(&p->ev_x[k], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&p->ev_hyb[k], cudaEventDisableTiming) != cudaSuccess)
-                return bail(fail(BFSM_ERR_CUDA, "cudaEventCreate failed"));
-    }
     if ((rc = relayout(p))) return bail(rc); // unit table, slot layout, partial-sum slots S
     if ((rc = do_configure(p))) return bail(rc);
     *out = p;
@@ -1068,11 +1013,6 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
         if (p->ev_nyq[k]) cudaEventDestroy(p->ev_nyq[k]);
     }
     if (p->side) cudaStreamDestroy(p->side);
-    if (p->xs) cudaStreamDestroy(p->xs);
-    for (int k = 0; k < 2; ++k) {
-        if (p->ev_x[k]) cudaEventDestroy(p->ev_x[k]);
-        if (p->ev_hyb[k]) cudaEventDestroy(p->ev_hyb[k]);
-    }
     lanes_free(p);
     for (int k = 0; k < bfsm_plan::MAX_LANES; ++k) {
         if (p->lanes[k].main) cudaStreamDestroy(p->lanes[k].main);
@@ -1202,7 +1142,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : 1;
     info->pencil_kernel = !p->packed ? 0 : p->pencil_kernel;
     info->batch_lanes_used = p->lanes_used_last;
-    info->gain_pipeline = p->fused ? 2 : (p->split ? 3 : 1);
+    info->gain_pipeline = p->fused ? 2 : 1;
     info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
 }
@@ -1244,7 +1184,6 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
         p->lanes_used_last = nl;
         CUDA_TRY(cudaEventRecord(p->ev_fork, st));
         for (int k = 0; k < nl; ++k) CUDA_TRY(cudaStreamWaitEvent(p->lanes[k].main, p->ev_fork, 0));
-        p->profiling_serial = true; // lanes run the unsplit pipeline (one hybrid buffer each)
         for (int c = 0; c < n_cells && !rc; ++c) {
             const int k = c % nl;
             lane_activate(p, k);
@@ -1253,7 +1192,6 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
             if (!rc) rc = do_finish(p, Q_dev + (size_t)c * N3, p->qhat, f_dev + (size_t)c * N3, ls);
         }
         lane_activate(p, 0);
-        p->profiling_serial = false;
         for (int k = 0; k < nl; ++k) {
             CUDA_TRY(cudaEventRecord(p->lanes[k].done, p->lanes[k].main));
             CUDA_TRY(cudaStreamWaitEvent(st, p->lanes[k].done, 0));

@@ -36,6 +36,7 @@
 // (validated against the unpacked path and the oracle with non-band-limited noise input).
 #pragma once
 #include "bfsm_fft.cuh"
+#include "bfsm_pencil_reg.cuh"
 
 namespace bfsm {
 
@@ -909,7 +910,7 @@ k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stri
         const cplx *__restrict__ qhat, const cplx *__restrict__ fhat,
         const double *__restrict__ beta2, const cplx *__restrict__ twtab, cplx *__restrict__ dst,
         const int *__restrict__ n_partials_item = nullptr, const double *__restrict__ src_real2 = nullptr,
-        int n_partials2 = 0)
+        int n_partials2 = 0, const int *__restrict__ n_partials2_item = nullptr)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B, TG = N * B;
     constexpr size_t N3 = (size_t)N * N * N;
@@ -922,14 +923,15 @@ k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stri
 
     if (MODE == PLANE_REAL) {
         // fixed-order sum of the partial slots: `n_partials` (or this item's own count) slots of
-        // src_real, then n_partials2 slots of src_real2
+        // src_real, then n_partials2 (or this item's own count) slots of src_real2
         const double *s = src_real + (size_t)item * N3 + (size_t)i * N * N;
         const double *s2 = src_real2 + (size_t)item * N3 + (size_t)i * N * N;
         const int np = n_partials_item ? __ldg(&n_partials_item[item]) : n_partials;
+        const int np2 = n_partials2_item ? __ldg(&n_partials2_item[item]) : n_partials2;
         z1_pass<N, SIGN, TG>(buf, tw, tg, [&](int j, int k) {
             double v = 0.0;
             for (int gq = 0; gq < np; ++gq) v += s[(size_t)gq * partial_stride + j * N + k];
-            for (int gq = 0; gq < n_partials2; ++gq) v += s2[(size_t)gq * partial_stride + j * N + k];
+            for (int gq = 0; gq < np2; ++gq) v += s2[(size_t)gq * partial_stride + j * N + k];
             return make_double2(v, 0.0);
         });
     } else {
@@ -1093,17 +1095,19 @@ __global__ void k_extract_nyq(const cplx *__restrict__ fhat, cplx *__restrict__ 
     nyq[t] = fhat[src];
 }
 
-// k_nyq_accum: S2_r += sum_s Re(Y_s^2), Y_s = (-1)^x U_s(y,z) + (-1)^y V_s(x,z) + (-1)^z W_s(x,y)
-// (sqrt(w_s) already folded into U,V,W).  grid (tiles of 16^3 outputs, GY); block 256 threads,
-// each owning the 2 x 2 x 4 brick x in {bx,bx+1}, y in {by,by+1}, z in {zq, zq+4, zq+8, zq+12}
-// (even bx, by: the x/y signs are compile-time; the z sign is a per-thread constant).  CTA (tile,gy)
-// covers share gy of the chunk's pairs and owns partial slot gy of S2 -- no atomics.  The 16 x 16
-// slices of U, V, W stream through a 3-stage cp.async ring: one barrier per pair.
-template <int N, bool ONE_SLOT = false>
+// k_nyq_accum: S2[slot][r] = sum_s Re(Y_s^2) over the pairs of one work unit,
+//   Y_s = (-1)^x U_s(y,z) + (-1)^y V_s(x,z) + (-1)^z W_s(x,y)     (sqrt(w_s) already folded into U,V,W).
+// grid (tiles of 16^3 outputs, work units of the launch); block 256 threads, each owning the 2 x 2 x 4
+// brick x in {bx,bx+1}, y in {by,by+1}, z in {zq, zq+4, zq+8, zq+12} (even bx, by: the x/y signs are
+// compile-time; the z sign is a per-thread constant).  A work unit is a run of pairs of ONE radius
+// (the same unit table as the register-resident x stage, bfsm_pencil_reg.cuh); CTA (tile, unit) stores
+// its sums into partial slot `slot` of that radius -- every (slot, radius, tile) is written exactly
+// once, so there is nothing to clear and no read-modify-write.  The 16 x 16 slices of U, V, W stream
+// through a 3-stage cp.async ring: one barrier per pair.
+template <int N>
 __global__ void __launch_bounds__(256, 2)
-k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
-            const int *__restrict__ r_end, double *__restrict__ S2, int pair0, int n_pairs_chunk,
-            int n_r_local)
+k_nyq_accum(const cplx *__restrict__ uvw, int uvw_pair0, const PencilUnit *__restrict__ units,
+            double *__restrict__ S2, int n_r_local)
 {
     constexpr int NT = 16, TPD = N / NT, PADR = NT + 2, STAGES = 3;
     constexpr size_t N3 = (size_t)N * N * N;
@@ -1114,74 +1118,64 @@ k_nyq_accum(const cplx *__restrict__ uvw, const int *__restrict__ pair_r,
     const int zq = t % 4, by = 2 * ((t / 4) % 8), bx = 2 * (t / 32);
     const double sz = (zq & 1) ? -1.0 : 1.0;
     const int la = t / NT, lb = t % NT; // element of the 16 x 16 slices this thread stages
-    const int G = gridDim.y;
-    const int lo = (int)(((long long)n_pairs_chunk * blockIdx.y) / G);
-    const int hi = (int)(((long long)n_pairs_chunk * (blockIdx.y + 1)) / G);
+    const PencilUnit un = units[blockIdx.y];
+    const int n_mine = un.p1 - un.p0;
 
-    // U[y][z], V[x][z], W[x][y] tiles of pair q -> ring slot
-    auto issue = [&](int q, int slot) {
-        const cplx *base = uvw + (size_t)q * 3 * N * N;
+    // U[y][z], V[x][z], W[x][y] tiles of pair un.p0 + n -> ring slot
+    auto issue = [&](int n, int slot) {
+        const cplx *base = uvw + (size_t)(un.p0 - uvw_pair0 + n) * 3 * N * N;
         cp_async16(&ring[slot][0][la][lb], base + (size_t)(ty0 + la) * N + tz0 + lb);
         cp_async16(&ring[slot][1][la][lb], base + (size_t)N * N + (size_t)(tx0 + la) * N + tz0 + lb);
         cp_async16(&ring[slot][2][la][lb], base + (size_t)2 * N * N + (size_t)(tx0 + la) * N + ty0 + lb);
     };
 
     double acc[2][2][4];
-    int p = lo;
-    while (p < hi) {
-        const int r = pair_r[pair0 + p];
-        int seg_end = r_end[r] - pair0;
-        if (seg_end > hi) seg_end = hi;
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < 2; ++b)
 #pragma unroll
-                for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
-        const int n_mine = seg_end - p;
-        __syncthreads(); // ring free (previous segment fully consumed)
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.0;
 #pragma unroll
-        for (int s0 = 0; s0 < STAGES - 1; ++s0) {
-            if (s0 < n_mine) issue(p + s0, s0);
-            cp_async_commit();
-        }
-        for (int n = 0; n < n_mine; ++n) {
-            cp_async_wait<STAGES - 2>();
-            __syncthreads(); // pair n landed for everybody; slot of pair n-1 is free again
-            if (n + STAGES - 1 < n_mine) issue(p + n + STAGES - 1, (n + STAGES - 1) % STAGES);
-            cp_async_commit();
-            const cplx(*sU)[PADR] = ring[n % STAGES][0];
-            const cplx(*sV)[PADR] = ring[n % STAGES][1];
-            const cplx(*sW)[PADR] = ring[n % STAGES][2];
-#pragma unroll
-            for (int a = 0; a < 2; ++a)
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {
-                    const cplx w0 = sW[bx + a][by + b];
-                    // fold the x sign into everything: Y^2 is even in Y, so use (-1)^x Y
-                    const double wr = (a ? -sz : sz) * w0.x, wi = (a ? -sz : sz) * w0.y;
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const cplx uu = sU[by + b][zq + 4 * c], vv = sV[bx + a][zq + 4 * c];
-                        // (-1)^x Y = U + (-1)^(x+y) V + (-1)^(x+z) W
-                        const double yr = uu.x + ((a ^ b) ? -vv.x : vv.x) + wr;
-                        const double yi = uu.y + ((a ^ b) ? -vv.y : vv.y) + wi;
-                        acc[a][b][c] = fma(yr, yr, acc[a][b][c]);
-                        acc[a][b][c] = fma(-yi, yi, acc[a][b][c]);
-                    }
-                }
-        }
-        cp_async_wait<0>();
-        double *Sr = S2 + ((size_t)(ONE_SLOT ? 0 : blockIdx.y) * n_r_local + r) * N3;
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-            for (int b = 0; b < 2; ++b)
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    Sr[((size_t)(tx0 + bx + a) * N + ty0 + by + b) * N + tz0 + zq + 4 * c] += acc[a][b][c];
-        p = seg_end;
+    for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+        if (s0 < n_mine) issue(s0, s0);
+        cp_async_commit();
     }
+    for (int n = 0; n < n_mine; ++n) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads(); // pair n landed for everybody; slot of pair n-1 is free again
+        if (n + STAGES - 1 < n_mine) issue(n + STAGES - 1, (n + STAGES - 1) % STAGES);
+        cp_async_commit();
+        const cplx(*sU)[PADR] = ring[n % STAGES][0];
+        const cplx(*sV)[PADR] = ring[n % STAGES][1];
+        const cplx(*sW)[PADR] = ring[n % STAGES][2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                const cplx w0 = sW[bx + a][by + b];
+                // fold the x sign into everything: Y^2 is even in Y, so use (-1)^x Y
+                const double wr = (a ? -sz : sz) * w0.x, wi = (a ? -sz : sz) * w0.y;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const cplx uu = sU[by + b][zq + 4 * c], vv = sV[bx + a][zq + 4 * c];
+                    // (-1)^x Y = U + (-1)^(x+y) V + (-1)^(x+z) W
+                    const double yr = uu.x + ((a ^ b) ? -vv.x : vv.x) + wr;
+                    const double yi = uu.y + ((a ^ b) ? -vv.y : vv.y) + wi;
+                    acc[a][b][c] = fma(yr, yr, acc[a][b][c]);
+                    acc[a][b][c] = fma(-yi, yi, acc[a][b][c]);
+                }
+            }
+    }
+    cp_async_wait<0>();
+    double *Sr = S2 + ((size_t)un.slot * n_r_local + un.r) * N3;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                Sr[((size_t)(tx0 + bx + a) * N + ty0 + by + b) * N + tz0 + zq + 4 * c] = acc[a][b][c];
 }
 
 } // namespace bfsm

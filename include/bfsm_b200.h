@@ -81,24 +81,22 @@ typedef struct {
     int chunk_pairs;       /* pairs per launch of the gain kernels; 0 = heuristic */
     int pencil_kernel;     /* x stage (packed mode): 0 = default, 1 = staged through a cp.async ring in
                               shared memory, 2 = register resident (no shared memory, LDG + SHFL) */
-    int seg_pairs;         /* register-resident x stage: pairs per work unit (one partial slot each);
-                              0 = heuristic */
+    int seg_pairs;         /* pairs per work unit of the register-resident x stage and of the Nyquist
+                              accumulate (one partial slot per unit of a radius); 0 = heuristic */
     int plane_kernel;      /* (y,z) stage (packed mode): 0 = default, 1 = k_plane_gain3 (every warp runs
                               all three stages), 2 = k_plane_gain_ws (warp-specialised pipeline, 64^3) */
-    int nyq_groups;        /* pair groups (= partial slots) of the Nyquist accumulate; 0 = heuristic */
     int side_stream;       /* 1: Nyquist accumulate on an internal side stream (default), 0: in line */
     int batch_lanes;       /* cells kept in flight by bfsm_collide(n_cells > 1): 1..4, 0 = default (4) */
     int gain_ctas;         /* persistent CTAs of k_plane_gain3; 0 = SMs x occupancy */
     int gain_pipeline;     /* 0 = default, 1 = one plane + one x kernel per chunk (hybrid grids through
                               HBM), 2 = fused persistent kernel (64^3 packed mode only): plane, Nyquist and
-                              x roles on disjoint SMs, hybrid grids through an L2-resident ring, 3 = split:
-                              the plane kernel of chunk c+1 and the x stage of chunk c run side by side on
-                              two streams and disjoint SMs (two hybrid scratch buffers, through HBM) */
+                              x roles on disjoint SMs, hybrid grids through an L2-resident ring (opt-in:
+                              measured slower than pipeline 1) */
     int fused_sub_pairs;   /* fused kernel: pairs per hand-over (sub-chunk); 0 = default */
     int fused_ring;        /* fused kernel: ring slots (sub-chunks in flight); 0 = default (2) */
-    int fused_pencil_ctas; /* fused / split pipeline: SMs left to the x stage; 0 = default */
+    int fused_pencil_ctas; /* fused kernel: CTAs (= SMs) of the x role; 0 = default */
     int fused_nyq_ctas;    /* fused kernel: CTAs of the Nyquist-plane role, a multiple of 3; 0 = default */
-    int reserved[2];
+    int reserved[3];
 } bfsm_plan_options;
 
 void bfsm_plan_options_init(bfsm_plan_options *opts);
@@ -167,7 +165,7 @@ typedef struct {
     int pencil_kernel;       /* x stage in use: 0 k_pencil_gain (unpacked mode), 1 k_pencil_gain_async
                                 (cp.async ring), 2 k_pencil_gain_reg (register resident) */
     int batch_lanes_used;    /* lanes the last bfsm_collide(n_cells > 1) ran on (1 before any) */
-    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel, 3 = split */
+    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);

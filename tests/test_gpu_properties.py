@@ -201,22 +201,24 @@ def test_deterministic_and_chunk_independent():
     assert rel_linf(c, a) <= 1e-13
 
 
-@pytest.mark.parametrize("knobs", [{"plane_kernel": 1}, {"pencil_kernel": 1}, {"pencil_kernel": 1, "plane_kernel": 1},
+@pytest.mark.parametrize("knobs", [{"plane_kernel": 1}, {"pencil_kernel": 2}, {"pencil_kernel": 2, "plane_kernel": 1},
                                    {"seg_pairs": 5}, {"side_stream": 0}, {"chunk_pairs": 7},
-                                   {"chunk_pairs": 7, "pencil_kernel": 1}, {"nyq_groups": 3}],
+                                   {"chunk_pairs": 7, "pencil_kernel": 2}, {"gain_pipeline": 2},
+                                   {"gain_pipeline": 2, "fused_sub_pairs": 5, "fused_ring": 3}],
                          ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
 def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
     """Every selectable kernel variant of the 64^3 path (bfsm_plan_options: the warp-specialised
-    pipelined plane kernel = default vs the 3-stage plane kernel, the register-resident x stage =
-    default vs the cp.async-staged one, odd work-unit sizes, the Nyquist accumulate on the main
-    stream, a chunk size that is not a multiple of the pairs per radius) computes the same Q: each one
+    pipelined plane kernel = default vs the 3-stage plane kernel, the cp.async-staged x stage =
+    default vs the register-resident one, odd work-unit sizes, the Nyquist accumulate on the main
+    stream, a chunk size that is not a multiple of the pairs per radius, the fused persistent gain
+    kernel with two ring geometries) computes the same Q: each one
     against the CPU oracle on the non-band-limited input, and against the default variant to a few
     ulps.  No variant uses atomics: repeated evaluations are bitwise identical."""
     Nv, n_r, n_s = 64, 2, 12
     f = make_input("noise", Nv)
     op0, gl, sd = make_operator(Nv, n_r, n_s)
     assert op0.info()["plane_kernel"] == 2          # k_plane_gain_ws is the default at 64^3
-    assert op0.info()["pencil_kernel"] == 2         # k_pencil_gain_reg is the default x stage
+    assert op0.info()["pencil_kernel"] == 1         # k_pencil_gain_async is the default x stage at 64^3
     q0 = _eval(op0, f)
     op1, _, _ = make_operator(Nv, n_r, n_s, options=knobs)
     for key, val in knobs.items():
