@@ -20,7 +20,14 @@ Extra objects on the JSON line (see DESIGN.md "Measurement"):
                stand-in) timed on the host cores on a bounded sample of the same workload
   e2e          same metric through the public operator with HOST buffers (H2D + D2H inside)
 
+  parity       after the timed loop the Q it timed is compared with the committed golden vector of the
+               same input (tests/golden/port_q_cfg4.npz at the default workload): every rank checks,
+               the line carries the max over ranks -- a throughput number for a wrong Q is worthless
+
 `--impl reference` times only the reference CPU operator (rank 0) and prints the same line shape.
+Its `ms_per_step` is the time of the step it actually executes (a SAMPLE of the workload: all
+directions, a few radii); `value` is scaled to the full pair list; `config.sampled_pairs` and
+`config.scale` say by how much (cost per pair is uniform: see profiles/r02_reference_scaling.json).
 """
 import argparse
 import json
@@ -172,7 +179,8 @@ def reference_sample(Nv, n_r, n_s, steps, warmup, budget_s=25.0):
               f"({n_r_sample * n_s} of {n_r * n_s} pairs) per step, time scaled by {n_r}/{n_r_sample}; "
               f"{steps} steps after {warmup} warm-up, OMP_NUM_THREADS={threads}")
     return {"value": 1.0 / t_eval, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
-            "seconds_per_eval": t_eval, "ms_per_step_sample": 1e3 * t_sample}
+            "seconds_per_eval": t_eval, "ms_per_step_sample": 1e3 * t_sample, "sampled_radii": n_r_sample,
+            "label": label + ", extrapolated from the sample"}
 
 
 def run_reference(args):
@@ -185,10 +193,16 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
-        "ms_per_step": 1e3 * cb["seconds_per_eval"], "higher_is_better": True,
+        # the step that is executed and timed is the SAMPLE (all directions, `sampled_radii` radii)
+        "ms_per_step": cb["ms_per_step_sample"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
-                   "input": "maxmix(seed=1234)"},
+                   "input": "maxmix(seed=1234)", "sampled_radii": cb["sampled_radii"],
+                   "sampled_pairs": cb["sampled_radii"] * n_s, "pairs": n_r * n_s,
+                   "scale": n_r / cb["sampled_radii"],
+                   "value_is": "1 / (ms_per_step * scale): evals/s of the full pair list extrapolated from "
+                               "the sample (uniform cost per pair, profiles/r02_reference_scaling.json)",
+                   "fft": "shim radix-4 FFT, not FFTW (FFTW is not installed in this image)"},
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -198,6 +212,109 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------- B200 arm
+def golden_parity(workload, Nv, n_r, n_s, Q, seed=1234):
+    """relative L-infinity distance of Q (numpy, N^3) from the committed golden vector of this workload
+    and input (written by the C port of the reference algorithm, tests/golden/make_golden*.py): every
+    second point per axis elementwise, the rest through per-x-plane sums of Q and Q^2."""
+    import numpy as np
+    name = "port_q_cfg4.npz" if (Nv, n_r, n_s) == (64, 32, 192) else "port_q_workloads.npz"
+    path = os.path.join(ROOT, "tests", "golden", name)
+    if not os.path.exists(path):
+        return None
+    G = np.load(path)
+    key = f"Nv{Nv}_r{n_r}_s{n_s}_maxmix" + ("" if name == "port_q_cfg4.npz" else str(seed))
+    if key + "_Qsub" not in G:
+        return None
+    Q = np.asarray(Q).reshape(Nv, Nv, Nv)
+    st, qmax = int(G["stride"]), float(G[key + "_max"])
+    e1 = np.abs(Q[::st, ::st, ::st] - G[key + "_Qsub"]).max() / qmax
+    e2 = np.abs(Q.sum(axis=(1, 2)) - G[key + "_plane_sum"]).max() / (qmax * Nv * Nv)
+    e3 = np.abs((Q * Q).sum(axis=(1, 2)) - G[key + "_plane_sumsq"]).max() / (qmax ** 2 * Nv * Nv)
+    return float(max(e1, e2, e3))
+
+
+def ncu_summary():
+    for name in ("r02_ncu_summary.json", "r01_ncu_summary.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as fh:
+                return json.load(fh), name
+        except Exception:
+            continue
+    return {}, None
+
+
+def roofline_of(info, prof, Nv, value_units_per_s, cells_per_unit, capi, local_rank):
+    """Roofline object of the dominant gain kernel class from one profiled evaluation of ONE cell.
+
+    algorithmic bytes per evaluation (unit = one transformed pair):
+      plane kernel : fhat once per launch + one hybrid grid per pair (two in unpacked mode)
+                     + the three Nyquist fields per pair (packed mode)
+      x stage      : one hybrid grid per pair read (+ the partial slots written once per launch)
+    `value_units_per_s` is the bench value (cells or evaluations per second) -> whole-step figure."""
+    peaks, peak_src = measured_peaks()
+    N3 = Nv ** 3
+    pairs, chunk = info["pairs_local"], info["chunk_pairs"]
+    n_launch = max(1, (pairs + chunk - 1) // chunk)
+    arrays = 1 if info["packed"] else 2
+    bytes_plane = 16 * N3 * (arrays * pairs + n_launch) + (16 * 3 * Nv * Nv * pairs if info["packed"] else 0)
+    bytes_pencil = 16 * N3 * (arrays * pairs) + 8 * N3 * n_launch
+    fused = info["gain_pipeline"] == 2
+    plane_names = {0: "k_plane_gain", 1: "k_plane_gain3", 2: "k_plane_gain_ws"}
+    pencil_names = {0: "k_pencil_gain", 1: "k_pencil_gain_async", 2: "k_pencil_gain_reg"}
+    if fused:
+        cls, kernel_name, bytes_cls = "plane_gain", "k_gain_fused", bytes_plane + bytes_pencil
+    elif prof["plane_gain"][0] >= prof["pencil_gain"][0]:
+        cls, kernel_name, bytes_cls = "plane_gain", plane_names[info["plane_kernel"]], bytes_plane
+    else:
+        cls, kernel_name, bytes_cls = "pencil_gain", pencil_names[info["pencil_kernel"]], bytes_pencil
+    ms, launches = prof[cls]
+    achieved = bytes_cls / (ms * 1e-3) / 1e9
+    summary, summary_name = ncu_summary()
+    cap = summary.get("full_capture_" + kernel_name) if Nv == 64 else None
+    traffic = None
+    if cap and "dram_bytes_read" in cap:
+        per_pair = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["pairs_in_launch"]
+        traffic = per_pair * pairs / launches
+    fp64_view = None
+    try:
+        peak_dfma = capi.measure_fp64_peak(local_rank)
+        plane_cap = summary.get("full_capture_" + plane_names[info["plane_kernel"]], {})
+        inst_per_pair = plane_cap.get("fp64_inst_per_pair", 10.2e6) * (N3 / 64 ** 3)
+        rate = inst_per_pair * pairs / (prof["plane_gain"][0] * 1e-3)
+        fp64_view = {"peak_dfma_per_s_measured": peak_dfma, "peak_tflops_measured": 2 * peak_dfma / 1e12,
+                     "plane_kernel_fp64_inst_per_s": rate, "frac_of_issue_peak": rate / peak_dfma,
+                     "note": "fp64 instructions (DADD/DMUL/DFMA each count 1) issued per second by the plane "
+                             "kernel (ncu count at 64^3, scaled by N^3) over the measured DFMA issue rate"}
+    except Exception as exc:  # measurement aid only
+        fp64_view = {"error": str(exc)}
+    contract_bytes = 96 * N3 * info["pairs_total"] + 128 * N3
+    step_bytes = (bytes_plane + bytes_pencil) * cells_per_unit
+    return {
+        "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"],
+        "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+        "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
+        else "fallback 6.65 TB/s (B200_PROFILING.md)",
+        "bytes_per_launch": bytes_cls / launches, "ms_per_launch": ms / launches,
+        "launches_per_eval": launches,
+        "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
+        "traffic_source": summary_name,
+        "note": "achieved = algorithmic bytes of the dominant gain kernel class of ONE evaluation / its summed "
+                "CUDA-event time (bfsm_collide_profiled, events on the launching stream); the Nyquist class "
+                "runs on a side stream, so class times do not add up to the step",
+        "pipeline_hbm": {
+            "bytes_per_unit": step_bytes, "achieved_gbs": step_bytes * value_units_per_s / 1e9,
+            "frac": step_bytes * value_units_per_s / 1e9 / peaks["hbm_gbs"],
+            "what": "algorithmic bytes of both gain kernels per benchmark unit x units/s (whole step)"},
+        "fp64": fp64_view,
+        "survey_contract": {
+            "bytes_per_eval": contract_bytes, "P_done": info["pairs_total"], "folded": bool(info["folded"]),
+            "equivalent_gbs": contract_bytes * cells_per_unit * value_units_per_s / 1e9,
+            "equivalent_frac": contract_bytes * cells_per_unit * value_units_per_s / 1e9 / peaks["hbm_gbs"],
+            "what": "SURVEY section 8(d) contract figure 96 N^3 P_done + 128 N^3: what a path without the "
+                    "restructurings (one forward FFT per radius, Hermitian packing) would move"},
+    }
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -205,6 +322,7 @@ def run_b200(args):
     import bfsm_b200 as B
     inp = B.inputs
     D = B.submodule("distributed")
+    capi = B.submodule("_capi")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -223,24 +341,47 @@ def run_b200(args):
     gl = B.GaussLegendreQuadrature(n_r, 0.0, inp.R_SUPPORT)
     sd = B.SphericalDesign(n_s)
     cells_total = BATCH_CELLS.get(args.workload, 0)
-    if cells_total:
-        return run_b200_batch(args, B, D, torch, dist, world, rank, local_rank, dev, cells_total)
-    op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
-                                 inp.L_DOMAIN, device=local_rank, shard_index=rank, shard_count=world)
+    batch = cells_total > 0
+
+    # ---- the operator, its inputs and one step
+    if batch:
+        # BASELINE config 5: independent cells, sharded by cell, no collective
+        lo, hi = D.shard_cells(cells_total, rank, world)
+        n_local = hi - lo
+        op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
+                                     inp.L_DOMAIN, device=local_rank)
+        base = np.stack([inp.maxmix(Nv, 1234 + c) for c in range(8)]).reshape(8, -1)
+        seeds = [1234 + ((lo + c) % 8) for c in range(n_local)]
+        f_np = np.stack([base[(lo + c) % 8] for c in range(n_local)]).reshape(-1) if n_local else np.zeros(0)
+        comm = None
+        units_per_step, unit_cells = cells_total, 1
+    else:
+        # BASELINE config 4: one evaluation, its (r, sigma) pairs sharded over the ranks, ONE all-reduce
+        n_local = 1
+        op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
+                                     inp.L_DOMAIN, device=local_rank, shard_index=rank, shard_count=world)
+        f_np = inp.maxmix(Nv).reshape(-1)
+        seeds = [1234]
+        comm = None
+        units_per_step, unit_cells = 1, 1
     op.initialize()
+    if not batch and world > 1:
+        comm = D.NcclCommunicator(local_rank)     # ncclComm_t owned by the C library (bfsm_comm)
     info = op.info()
 
-    f_host = torch.from_numpy(inp.maxmix(Nv)).reshape(-1).pin_memory()
-    q_host = torch.empty(N3, dtype=torch.float64).pin_memory()
+    f_host = torch.from_numpy(np.ascontiguousarray(f_np)).pin_memory()
+    q_host = [torch.empty(n_local * N3, dtype=torch.float64).pin_memory() for _ in range(2)]
     f_dev = f_host.to(dev)
     q_dev = torch.empty_like(f_dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
 
-    if world > 1:
-        sharded = D.PairShardedCollision(op, N3)
-
+    if batch:
         def step():
-            sharded(q_dev, f_dev)
+            if n_local:
+                op(q_dev, f_dev, n_cells=n_local)
+    elif world > 1:
+        def step():
+            op.collide_sharded(q_dev, f_dev, comm)   # bfsm_collide_sharded: kernels + ncclAllReduce in C
     else:
         def step():
             op(q_dev, f_dev)
@@ -249,6 +390,12 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -279,231 +426,89 @@ def run_b200(args):
         b.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / steps
-    value = 1e3 / ms_per_step
+    ms_per_step = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev)) / steps
+    value = units_per_step * 1e3 / ms_per_step
 
-    # ---- end to end through the public operator with HOST buffers (H2D + D2H inside)
-    e2e_steps = steps
-    if world > 1:
-        def e2e_step():
-            f_dev.copy_(f_host, non_blocking=True)
-            sharded(q_dev, f_dev)
-            q_host.copy_(q_dev, non_blocking=True)
-            torch.cuda.synchronize()
-    else:
-        f_np, q_np = f_host.numpy(), q_host.numpy()
+    # ---- parity of what was just timed: q_dev against the committed golden vectors
+    q_timed = q_dev.cpu().numpy().reshape(max(n_local, 1), -1) if n_local else np.zeros((0, N3))
+    errs = [golden_parity(args.workload, Nv, n_r, n_s, q_timed[c], seeds[c])
+            for c in range(min(n_local, 8))]
+    errs = [e for e in errs if e is not None]
+    parity_dev = max_over_ranks(max(errs) if errs else -1.0)
 
-        def e2e_step():
-            op(q_np, f_np)      # bfsm_collide_host: H2D, evaluate, D2H, stream sync
-    e2e_step()
+    # ---- end to end through the public operator with HOST buffers: every step copies its input from
+    # pinned host memory and its result back; two steps in flight (bfsm_collide_host_async)
+    def e2e_step(k):
+        if n_local:
+            op.submit_host(q_host[k & 1], f_host, comm=comm, n_cells=n_local)
+    for k in range(2):
+        e2e_step(k)
+    op.flush_host()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for k in range(steps):
+        e2e_step(k)
+    op.flush_host()
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = e2e_steps / float(t.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = units_per_step * steps / e2e_s
+    q_e2e = q_host[(steps - 1) & 1].numpy().reshape(max(n_local, 1), -1) if n_local else np.zeros((0, N3))
+    errs = [golden_parity(args.workload, Nv, n_r, n_s, q_e2e[c], seeds[c]) for c in range(min(n_local, 8))]
+    errs = [e for e in errs if e is not None]
+    parity_e2e = max_over_ranks(max(errs) if errs else -1.0)
 
-    # ---- roofline of the dominant kernel class, measured live with CUDA events
+    # ---- roofline of the dominant kernel class, measured live with CUDA events (one cell, rank 0)
     roofline = None
-    prof = None
     if world == 1:
-        op.profile(q_dev, f_dev)
-        prof = op.profile(q_dev, f_dev)
-        peaks, peak_src = measured_peaks()
-        pairs, chunk = info["pairs_local"], info["chunk_pairs"]
-        n_launch = (pairs + chunk - 1) // chunk
-        arrays = 1 if info["packed"] else 2      # 3-D arrays transformed per pair
-        # algorithmic bytes per evaluation of each gain kernel:
-        #   k_plane_gain : read fhat once per launch, write `arrays` hybrid grids per pair
-        #                  (+ the three Nyquist planes per pair in packed mode)
-        #   k_pencil_gain: read `arrays` hybrid grids per pair, read+write S_r once per launch
-        bytes_plane = 16 * N3 * (arrays * pairs + n_launch) + (16 * 3 * Nv * Nv * pairs if info["packed"] else 0)
-        bytes_pencil = 16 * N3 * (arrays * pairs) + 16 * N3 * n_launch
-        cls = "plane_gain" if prof["plane_gain"][0] >= prof["pencil_gain"][0] else "pencil_gain"
-        ms, launches = prof[cls]
-        bytes_cls = bytes_plane if cls == "plane_gain" else bytes_pencil
-        achieved = bytes_cls / (ms * 1e-3) / 1e9
-        plane_names = {0: "k_plane_gain", 1: "k_plane_gain3", 2: "k_plane_gain_ws"}
-        if cls == "plane_gain":
-            kernel_name = plane_names[info["plane_kernel"]]
-        else:
-            kernel_name = "k_pencil_gain_async" if info["packed"] else "k_pencil_gain"
-        plane_name = plane_names[info["plane_kernel"]]
-        contract_bytes = 96 * N3 * info["pairs_total"] + 128 * N3
-        # ncu figures of the gain kernels from the committed `ncu --set full` captures
-        # (profiles/r01_ncu_summary.json): DRAM bytes per launch (scaled to this run's pairs per
-        # launch) and fp64 instructions per pair
-        summary = {}
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as fh:
-                summary = json.load(fh)
-        except Exception:
-            summary = {}
-        cap = summary.get("full_capture_" + kernel_name) if Nv == 64 else None
-        traffic = None
-        if cap and "dram_bytes_read" in cap:
-            per_pair = (cap["dram_bytes_read"] + cap["dram_bytes_write"]) / cap["pairs_in_launch"]
-            traffic = per_pair * pairs / launches
-        # second view: the FP64 pipe (the plane kernel is LSU/FP64 limited, not HBM limited).
-        # fp64 instructions per pair of the plane kernel from the committed ncu capture, peak
-        # measured live by a DFMA micro-benchmark.
-        fp64_view = None
-        try:
-            capi = B.submodule("_capi")
-            peak_dfma = capi.measure_fp64_peak(local_rank)
-            plane_cap = summary.get("full_capture_" + plane_name, {})
-            inst_per_pair = plane_cap.get("fp64_inst_per_pair", 11.2e6) * (N3 / 64 ** 3)
-            rate = inst_per_pair * pairs / (prof["plane_gain"][0] * 1e-3)
-            fp64_view = {"peak_dfma_per_s_measured": peak_dfma, "peak_tflops_measured": 2 * peak_dfma / 1e12,
-                         "plane_kernel": plane_name, "plane_kernel_fp64_inst_per_s": rate,
-                         "frac_of_issue_peak": rate / peak_dfma,
-                         "note": "fp64 instructions (DADD/DMUL/DFMA each count 1) issued per second by "
-                                 "the plane kernel over the measured DFMA issue rate"}
-        except Exception as exc:  # measurement aid only
-            fp64_view = {"error": str(exc)}
-        note = summary.get("roofline_note", "see profiles/r01_ncu_summary.json")
-        roofline = {
-            "bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peaks["hbm_gbs"],
-            "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
-            "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured"
-            else "fallback 6.65 TB/s (B200_PROFILING.md)",
-            "bytes_per_launch": bytes_cls / launches, "ms_per_launch": ms / launches,
-            "launches_per_eval": launches,
-            # share of the timed step (the nyquist class runs on a side stream and overlaps, so the
-            # class times do not add up to the step)
-            "share_of_step": ms / ms_per_step,
-            "class_ms": {k: round(v[0], 4) for k, v in prof.items()},
-            "note": note,
-            "pipeline_hbm": {
-                "bytes_per_eval": bytes_plane + bytes_pencil,
-                "achieved_gbs": (bytes_plane + bytes_pencil) * value / 1e9,
-                "frac": (bytes_plane + bytes_pencil) * value / 1e9 / peaks["hbm_gbs"],
-                "what": "algorithmic bytes of both gain kernels per evaluation x evals/s (whole step)"},
-            "fp64": fp64_view,
-            "survey_contract": {
-                "bytes_per_eval": contract_bytes, "P_done": info["pairs_total"],
-                "folded": bool(info["folded"]),
-                "equivalent_gbs": contract_bytes * value / 1e9,
-                "equivalent_frac": contract_bytes * value / 1e9 / peaks["hbm_gbs"],
-            },
-        }
+        f1, q1 = f_dev[:N3], torch.empty(N3, dtype=torch.float64, device=dev)
+        op.profile(q1, f1)
+        prof = op.profile(q1, f1)
+        roofline = roofline_of(info, prof, Nv, value, 1, capi, local_rank)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cb = reference_sample(Nv, n_r, n_s, steps=2, warmup=1, budget_s=25.0)
-        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "label")}
 
     if rank == 0:
+        parity = {"rel_linf_device_path": parity_dev if parity_dev >= 0 else None,
+                  "rel_linf_e2e_path": parity_e2e if parity_e2e >= 0 else None, "tolerance": 1e-12,
+                  "against": "tests/golden/port_q_cfg4.npz | port_q_workloads.npz (C port of the reference "
+                             "algorithm, same maxmix input), max over ranks and checked cells"}
+        parity["ok"] = all(v is not None and v <= 1e-12 for v in
+                           (parity["rel_linf_device_path"], parity["rel_linf_e2e_path"]))
+        config = {
+            "workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
+            "pairs_transformed": info["pairs_total"], "antipodal_folding": bool(info["folded"]),
+            "hermitian_packing": bool(info["packed"]), "chunk_pairs": info["chunk_pairs"],
+            "gain_pipeline": info["gain_pipeline"], "plane_kernel": info["plane_kernel"],
+            "pencil_kernel": info["pencil_kernel"],
+        }
+        if batch:
+            config.update({"input": "maxmix(seed=1234+c), 8 distinct cells tiled", "cells_per_step": cells_total,
+                           "cells_per_rank": n_local, "parallelism": f"cell-shard x{world}",
+                           "l2_flush": "256 MiB written between steps (untimed); each step streams >> L2"})
+        else:
+            config.update({"input": "maxmix(seed=1234)",
+                           "parallelism": f"pair-shard x{world}, ncclAllReduce of N^3 doubles inside "
+                                          "bfsm_collide_sharded" if world > 1 else "single GPU",
+                           "l2_flush": "256 MiB written between steps (untimed); each evaluation streams "
+                                       ">> 126 MB through L2"})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
-                "input": "maxmix(seed=1234)", "pairs_transformed": info["pairs_total"],
-                "antipodal_folding": bool(info["folded"]), "hermitian_packing": bool(info["packed"]),
-                "chunk_pairs": info["chunk_pairs"],
-                "parallelism": f"pair-shard x{world}" if world > 1 else "single GPU",
-                "l2_flush": "256 MiB written between steps (untimed); each evaluation streams "
-                            ">> 126 MB through L2",
-            },
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N3,
-                    "d2h_bytes_per_step": 8 * N3},
-            "gpu_launches": info["launches_per_cell"] * steps,
-            "roofline": roofline,
-            "cpu_baseline": cpu_baseline,
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N3 * n_local,
+                    "d2h_bytes_per_step": 8 * N3 * n_local,
+                    "how": "op.submit_host per step (pinned host buffers, H2D + kernels + D2H, two steps in "
+                           "flight), flush at the end; wall clock, max over ranks"},
+            "gpu_launches": info["launches_per_cell"] * max(n_local, 1) * steps,
+            "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
-    return 0
-
-
-def run_b200_batch(args, B, D, torch, dist, world, rank, local_rank, dev, cells_total):
-    """BASELINE config 5: `cells_total` independent cells per step, cell-sharded, no collective."""
-    import numpy as np
-    inp = B.inputs
-    Nv, n_r, n_s = WORKLOADS[args.workload]
-    N3 = Nv ** 3
-    steps, warmup = max(1, args.steps), max(3, args.warmup)
-    lo, hi = D.shard_cells(cells_total, rank, world)
-    n_local = hi - lo
-    gl = B.GaussLegendreQuadrature(n_r, 0.0, inp.R_SUPPORT)
-    sd = B.SphericalDesign(n_s)
-    op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
-                                 inp.L_DOMAIN, device=local_rank)
-    op.initialize()
-    info = op.info()
-    # 8 distinct seeded cells, tiled (synthetic data of the named shape)
-    base = np.stack([inp.maxmix(Nv, 1234 + c) for c in range(8)]).reshape(8, -1)
-    f_host = torch.from_numpy(np.tile(base, (-(-n_local // 8), 1))[:n_local].copy()).reshape(-1).pin_memory()
-    q_host = torch.empty(n_local * N3, dtype=torch.float64).pin_memory()
-    f_dev = f_host.to(dev)
-    q_dev = torch.empty_like(f_dev)
-
-    def step():
-        op(q_dev, f_dev, n_cells=n_local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    for _ in range(warmup):
-        step()
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    for a, b in ev:
-        a.record()
-        step()
-        b.record()
-    barrier()
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_per_step = float(t.item()) / steps
-    value = cells_total * 1e3 / ms_per_step
-
-    f_np, q_np = f_host.numpy(), q_host.numpy()
-    op(q_np, f_np, n_cells=n_local)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        op(q_np, f_np, n_cells=n_local)     # host buffers: H2D + evaluate + D2H inside
-    barrier()
-    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = cells_total * steps / float(t.item())
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "Nv": Nv, "N_r": n_r, "N_sigma": n_s,
-                       "cells_per_step": cells_total, "cells_per_rank": n_local,
-                       "input": "maxmix(seed=1234+c), 8 distinct cells tiled",
-                       "pairs_transformed": info["pairs_total"], "parallelism": f"cell-shard x{world}",
-                       "l2_flush": "each step streams 512 cells x 190 MiB of scratch >> L2"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N3 * n_local,
-                    "d2h_bytes_per_step": 8 * N3 * n_local},
-            "gpu_launches": info["launches_per_cell"] * n_local * steps,
-            "roofline": None, "cpu_baseline": None}))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -8,7 +8,8 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libbfsm_b200.so")
 
-BFSM_OK, BFSM_ERR_INVALID, BFSM_ERR_UNSUPPORTED, BFSM_ERR_CUDA, BFSM_ERR_NOMEM = range(5)
+BFSM_OK, BFSM_ERR_INVALID, BFSM_ERR_UNSUPPORTED, BFSM_ERR_CUDA, BFSM_ERR_NOMEM, BFSM_ERR_COMM = range(6)
+BFSM_UNIQUE_ID_BYTES = 128
 BFSM_FLAG_NO_FOLD = 1
 BFSM_FLAG_NO_PACK = 2
 
@@ -19,7 +20,10 @@ EXPORTS = (
     "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
     "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host", "bfsm_measure_fp64_peak",
     "bfsm_debug_plane_work", "bfsm_debug_shares_aligned", "bfsm_debug_fail_lane_alloc", "bfsm_debug_units",
-    "bfsm_plan_options_init", "bfsm_plan_create_ex",
+    "bfsm_plan_options_init", "bfsm_plan_create_ex", "bfsm_comm_unique_id", "bfsm_comm_init_rank",
+    "bfsm_comm_init_all", "bfsm_comm_adopt", "bfsm_comm_destroy", "bfsm_collide_sharded",
+    "bfsm_collide_sharded_group", "bfsm_collide_partial", "bfsm_vec_axpby", "bfsm_moments",
+    "bfsm_collide_host_async", "bfsm_collide_host_flush",
 )
 
 KCLASS_NAMES = ("forward", "plane_gain", "pencil_gain", "accum", "final", "nyquist")
@@ -110,6 +114,32 @@ def load():
     lib.bfsm_plan_create_ex.argtypes = lib.bfsm_plan_create.argtypes + [ctypes.POINTER(PlanOptions)]
     lib.bfsm_plan_options_init.restype = None
     lib.bfsm_plan_options_init.argtypes = [ctypes.POINTER(PlanOptions)]
+    lib.bfsm_comm_unique_id.restype = ctypes.c_int
+    lib.bfsm_comm_unique_id.argtypes = [ctypes.c_char_p]
+    lib.bfsm_comm_init_rank.restype = ctypes.c_int
+    lib.bfsm_comm_init_rank.argtypes = [ctypes.POINTER(vp), ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.bfsm_comm_init_all.restype = ctypes.c_int
+    lib.bfsm_comm_init_all.argtypes = [ctypes.POINTER(vp), ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+    lib.bfsm_comm_adopt.restype = ctypes.c_int
+    lib.bfsm_comm_adopt.argtypes = [ctypes.POINTER(vp), vp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.bfsm_comm_destroy.restype = ctypes.c_int
+    lib.bfsm_comm_destroy.argtypes = [vp]
+    lib.bfsm_collide_sharded.restype = ctypes.c_int
+    lib.bfsm_collide_sharded.argtypes = [vp, vp, vp, vp, vp]
+    lib.bfsm_collide_sharded_group.restype = ctypes.c_int
+    lib.bfsm_collide_sharded_group.argtypes = [ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp),
+                                               ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    lib.bfsm_collide_partial.restype = ctypes.c_int
+    lib.bfsm_collide_partial.argtypes = [vp, vp, vp, vp]
+    lib.bfsm_collide_host_async.restype = ctypes.c_int
+    lib.bfsm_collide_host_async.argtypes = [vp, vp, vp, vp, ctypes.c_int, vp]
+    lib.bfsm_collide_host_flush.restype = ctypes.c_int
+    lib.bfsm_collide_host_flush.argtypes = [vp]
+    lib.bfsm_vec_axpby.restype = ctypes.c_int
+    lib.bfsm_vec_axpby.argtypes = [ctypes.c_int, vp, ctypes.c_double, vp, ctypes.c_double, vp,
+                                   ctypes.c_ulonglong, vp]
+    lib.bfsm_moments.restype = ctypes.c_int
+    lib.bfsm_moments.argtypes = [vp, vp, ctypes.c_int, vp, vp]
     lib.bfsm_debug_units.restype = ctypes.c_int
     lib.bfsm_debug_units.argtypes = [ctypes.c_int] * 5 + [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     lib.bfsm_debug_fail_lane_alloc.restype = ctypes.c_int

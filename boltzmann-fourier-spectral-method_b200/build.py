@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libbfsm_b200.so")
 SOURCES = ["bfsm_capi.cu"]
-HEADERS = ["bfsm_fft.cuh", "bfsm_kernels.cuh", os.path.join("..", "..", "include", "bfsm_b200.h")]
+HEADERS = ["bfsm_fft.cuh", "bfsm_kernels.cuh", "bfsm_pencil_reg.cuh", "bfsm_fused.cuh",
+           os.path.join("..", "..", "include", "bfsm_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -39,7 +40,7 @@ def build_library(force=False, verbose=False):
     """Compile csrc/*.cu into csrc/libbfsm_b200.so. Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-ldl"]
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a wrapper; let nvcc pick the system g++
     res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)

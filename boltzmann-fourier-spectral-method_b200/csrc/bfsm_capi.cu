@@ -4,6 +4,10 @@
 #include "bfsm_kernels.cuh"
 #include "bfsm_pencil_reg.cuh"
 #include "bfsm_fused.cuh"
+#include "bfsm_aux.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h> // types and enums only: the library is loaded with dlopen at first use
 
 #include <algorithm>
 #include <cmath>
@@ -107,6 +111,17 @@ struct bfsm_plan {
     cplx *qhat = nullptr;  // [N^3]
     double *stage_f = nullptr, *stage_q = nullptr; // host-pointer entry point staging
     size_t stage_cells = 0;
+    // pipelined host-pointer entry point (bfsm_collide_host_async): two staging slots, copies on their
+    // own streams so that the H2D of step k+1 and the D2H of step k-1 run under the kernels of step k
+    struct HostPipe {
+        double *f[2] = {nullptr, nullptr}, *q[2] = {nullptr, nullptr};
+        size_t cells = 0;
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr},
+                    out_done[2] = {nullptr, nullptr};
+        bool used[2] = {false, false};
+        unsigned long long submitted = 0;
+    } pipe;
     std::vector<void *> allocs;
 
     // Batch mode (n_cells > 1): up to n_lanes cells are kept in flight on "lanes", each with its own
@@ -558,16 +573,19 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     return BFSM_OK;
 }
 
-// loss term + inverse transform + combine (cpp:281-330); needs p->fhat of the same f
-template <int N> int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st)
+// loss term + inverse transform + combine (cpp:281-330); needs p->fhat of the same f.
+// with_loss = false: Q = Re(IFFT3(qhat)) only (a pair shard's partial gain, see bfsm_collide_sharded).
+template <int N>
+int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st, bool with_loss = true)
 {
     constexpr int TILES = N * N / TZ;
     constexpr int TGP = Geo<N>::B * TZ;
     {
         ProfSpan ps(p, st, BFSM_KCLASS_FINAL);
-        k_plane<N, +1, PLANE_FINAL><<<dim3(N, 2), N * Geo<N>::B, plane_smem<N>(), st>>>(
+        k_plane<N, +1, PLANE_FINAL><<<dim3(N, with_loss ? 2 : 1), N * Geo<N>::B, plane_smem<N>(), st>>>(
             nullptr, 0, 0, qhat, p->fhat, p->beta2, p->tw, p->tmp);
-        k_pencil_final<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, f, Q);
+        if (with_loss) k_pencil_final<N, true><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, f, Q);
+        else k_pencil_final<N, false><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, f, Q);
     }
     CUDA_TRY(cudaGetLastError());
     return BFSM_OK;
@@ -592,9 +610,9 @@ int do_gain_hat(bfsm_plan *p, cplx *qhat, const double *f, cudaStream_t st)
 {
     DISPATCH_N(p, run_gain_hat<N_>(p, qhat, f, st));
 }
-int do_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st)
+int do_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st, bool with_loss = true)
 {
-    DISPATCH_N(p, run_finish<N_>(p, Q, qhat, f, st));
+    DISPATCH_N(p, run_finish<N_>(p, Q, qhat, f, st, with_loss));
 }
 int do_configure(bfsm_plan *p) { DISPATCH_N(p, configure_kernels<N_>()); }
 int do_launch_count(const bfsm_plan *p) { DISPATCH_N(p, launches_per_cell<N_>(p)); }
@@ -1021,6 +1039,15 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->stage_f) cudaFree(p->stage_f);
     if (p->stage_q) cudaFree(p->stage_q);
+    for (int b = 0; b < 2; ++b) {
+        if (p->pipe.f[b]) cudaFree(p->pipe.f[b]);
+        if (p->pipe.q[b]) cudaFree(p->pipe.q[b]);
+        if (p->pipe.in_done[b]) cudaEventDestroy(p->pipe.in_done[b]);
+        if (p->pipe.comp_done[b]) cudaEventDestroy(p->pipe.comp_done[b]);
+        if (p->pipe.out_done[b]) cudaEventDestroy(p->pipe.out_done[b]);
+    }
+    if (p->pipe.h2d) cudaStreamDestroy(p->pipe.h2d);
+    if (p->pipe.d2h) cudaStreamDestroy(p->pipe.d2h);
     delete p;
     return BFSM_OK;
 }
@@ -1170,7 +1197,8 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
     if (n_cells < 0) return fail(BFSM_ERR_INVALID, "n_cells must be >= 0");
     if (p->shard_count != 1)
         return fail(BFSM_ERR_INVALID,
-                    "bfsm_collide needs an unsharded plan; use bfsm_gain_hat + all-reduce + bfsm_finish");
+                    "bfsm_collide needs an unsharded plan; use bfsm_collide_sharded (or bfsm_collide_partial / "
+                    "bfsm_gain_hat + your own reduction)");
     GuardDevice guard(p->device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     const size_t N3 = (size_t)p->N * p->N * p->N;
@@ -1232,6 +1260,77 @@ extern "C" int bfsm_collide_host(bfsm_plan *p, double *Q_host, const double *f_h
     if (rc) return rc;
     CUDA_TRY(cudaMemcpyAsync(Q_host, p->stage_q, bytes, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    return BFSM_OK;
+}
+
+// Pipelined host-pointer evaluation: returns once the step is enqueued (and the step submitted two
+// calls earlier has delivered its Q); bfsm_collide_host_flush waits for everything outstanding.
+extern "C" int bfsm_collide_host_async(bfsm_plan *p, bfsm_comm *cm, double *Q_host, const double *f_host,
+                                       int n_cells, void *stream)
+{
+    if (!p || !Q_host || !f_host) return fail(BFSM_ERR_INVALID, "NULL argument");
+    if (n_cells < 0) return fail(BFSM_ERR_INVALID, "n_cells must be >= 0");
+    if (n_cells == 0) return BFSM_OK;
+    if (p->shard_count > 1 && (n_cells != 1 || !cm))
+        return fail(BFSM_ERR_INVALID, "a sharded plan evaluates one cell per call and needs a communicator");
+    GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    bfsm_plan::HostPipe &hp = p->pipe;
+    const size_t N3 = (size_t)p->N * p->N * p->N;
+    const size_t bytes = sizeof(double) * N3 * (size_t)n_cells;
+    if (!hp.h2d) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.in_done[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.comp_done[b], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&hp.out_done[b], cudaEventDisableTiming));
+        }
+    }
+    if (hp.cells < (size_t)n_cells) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        for (int b = 0; b < 2; ++b) {
+            if (hp.f[b]) cudaFree(hp.f[b]);
+            if (hp.q[b]) cudaFree(hp.q[b]);
+            hp.f[b] = hp.q[b] = nullptr;
+            hp.used[b] = false;
+        }
+        hp.cells = 0;
+        for (int b = 0; b < 2; ++b) {
+            CUDA_TRY(cudaMalloc((void **)&hp.f[b], bytes));
+            CUDA_TRY(cudaMalloc((void **)&hp.q[b], bytes));
+        }
+        hp.cells = (size_t)n_cells;
+    }
+    const int b = (int)(hp.submitted & 1);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (hp.used[b]) {
+        // slot b was used by the step submitted two calls ago: its Q must have reached the host (that
+        // also means its kernels are done with f[b] and q[b])
+        CUDA_TRY(cudaEventSynchronize(hp.out_done[b]));
+    }
+    CUDA_TRY(cudaMemcpyAsync(hp.f[b], f_host, bytes, cudaMemcpyHostToDevice, hp.h2d));
+    CUDA_TRY(cudaEventRecord(hp.in_done[b], hp.h2d));
+    CUDA_TRY(cudaStreamWaitEvent(st, hp.in_done[b], 0));
+    int rc = (p->shard_count > 1) ? bfsm_collide_sharded(p, cm, hp.q[b], hp.f[b], stream)
+                                  : bfsm_collide(p, hp.q[b], hp.f[b], n_cells, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaEventRecord(hp.comp_done[b], st));
+    CUDA_TRY(cudaStreamWaitEvent(hp.d2h, hp.comp_done[b], 0));
+    CUDA_TRY(cudaMemcpyAsync(Q_host, hp.q[b], bytes, cudaMemcpyDeviceToHost, hp.d2h));
+    CUDA_TRY(cudaEventRecord(hp.out_done[b], hp.d2h));
+    hp.used[b] = true;
+    ++hp.submitted;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_collide_host_flush(bfsm_plan *p)
+{
+    if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
+    GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    for (int b = 0; b < 2; ++b)
+        if (p->pipe.used[b]) CUDA_TRY(cudaEventSynchronize(p->pipe.out_done[b]));
     return BFSM_OK;
 }
 
@@ -1306,6 +1405,242 @@ extern "C" int bfsm_copy_to_host(int device, void *dst_host, const void *src_dev
     GuardDevice guard(device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     CUDA_TRY(cudaMemcpy(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return BFSM_OK;
+}
+
+// =========================================================================== multi-GPU (NCCL)
+// The path's one exchange step: every rank evaluates its shard of the (r, sigma)
+// pair list, turns its partial gain spectrum into a partial Q in physical space (the inverse transform
+// is linear), rank 0 subtracts the loss term, and ONE ncclAllReduce of N^3 real doubles (2 MiB at
+// 64^3, half of the complex spectrum) leaves Q(f,f) on every rank -- nothing runs after the collective.
+// NCCL is bound at run time (dlopen "libnccl.so.2"): inside a PyTorch process that is the copy torch
+// already loaded, in a plain C++ host the system library.
+namespace {
+
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+NcclApi *nccl_api()
+{
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    auto sym = [&](const char *name) { return dlsym(h, name); };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommInitAll || !api.CommDestroy || !api.AllReduce ||
+        !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
+        return nullptr;
+    api.handle = h;
+    return &api;
+}
+
+#define NCCL_TRY(api, expr)                                                                    \
+    do {                                                                                       \
+        ncclResult_t r_ = (expr);                                                              \
+        if (r_ != ncclSuccess) {                                                               \
+            char buf_[512];                                                                    \
+            snprintf(buf_, sizeof buf_, "%s failed: %s", #expr, (api)->GetErrorString(r_));     \
+            return fail(BFSM_ERR_COMM, buf_);                                                  \
+        }                                                                                      \
+    } while (0)
+
+} // namespace
+
+struct bfsm_comm {
+    ncclComm_t comm = nullptr;
+    int n_ranks = 1, rank = 0, device = 0;
+    bool owned = true;
+};
+
+static_assert(BFSM_UNIQUE_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "unique id size");
+
+extern "C" int bfsm_comm_unique_id(unsigned char *id)
+{
+    if (!id) return fail(BFSM_ERR_INVALID, "id is NULL");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(BFSM_ERR_COMM, "NCCL (libnccl.so.2) could not be loaded");
+    ncclUniqueId uid;
+    NCCL_TRY(api, api->GetUniqueId(&uid));
+    std::memcpy(id, uid.internal, BFSM_UNIQUE_ID_BYTES);
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_comm_init_rank(bfsm_comm **out, const unsigned char *id, int n_ranks, int rank, int device)
+{
+    if (!out || !id) return fail(BFSM_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(BFSM_ERR_INVALID, "rank / n_ranks out of range");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(BFSM_ERR_COMM, "NCCL (libnccl.so.2) could not be loaded");
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    ncclUniqueId uid;
+    std::memcpy(uid.internal, id, BFSM_UNIQUE_ID_BYTES);
+    ncclComm_t c = nullptr;
+    NCCL_TRY(api, api->CommInitRank(&c, n_ranks, uid, rank));
+    bfsm_comm *cm = new bfsm_comm;
+    cm->comm = c; cm->n_ranks = n_ranks; cm->rank = rank; cm->device = device;
+    *out = cm;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_comm_init_all(bfsm_comm **comms, int n_devices, const int *devices)
+{
+    if (!comms || !devices || n_devices < 1) return fail(BFSM_ERR_INVALID, "bad argument");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(BFSM_ERR_COMM, "NCCL (libnccl.so.2) could not be loaded");
+    std::vector<ncclComm_t> raw(n_devices, nullptr);
+    NCCL_TRY(api, api->CommInitAll(raw.data(), n_devices, devices));
+    for (int k = 0; k < n_devices; ++k) {
+        bfsm_comm *cm = new bfsm_comm;
+        cm->comm = raw[k]; cm->n_ranks = n_devices; cm->rank = k; cm->device = devices[k];
+        comms[k] = cm;
+    }
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_comm_adopt(bfsm_comm **out, void *nccl_comm, int n_ranks, int rank, int device)
+{
+    if (!out || !nccl_comm) return fail(BFSM_ERR_INVALID, "NULL argument");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(BFSM_ERR_INVALID, "rank / n_ranks out of range");
+    if (!nccl_api()) return fail(BFSM_ERR_COMM, "NCCL (libnccl.so.2) could not be loaded");
+    bfsm_comm *cm = new bfsm_comm;
+    cm->comm = (ncclComm_t)nccl_comm; cm->n_ranks = n_ranks; cm->rank = rank; cm->device = device;
+    cm->owned = false;
+    *out = cm;
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_comm_destroy(bfsm_comm *cm)
+{
+    if (!cm) return BFSM_OK;
+    NcclApi *api = nccl_api();
+    if (cm->owned && cm->comm && api) {
+        GuardDevice guard(cm->device);
+        api->CommDestroy(cm->comm);
+    }
+    delete cm;
+    return BFSM_OK;
+}
+
+namespace {
+int check_shard(const bfsm_plan *p, const bfsm_comm *cm)
+{
+    if (!p || !cm) return fail(BFSM_ERR_INVALID, "NULL argument");
+    if (p->shard_count != cm->n_ranks || p->shard_index != cm->rank)
+        return fail(BFSM_ERR_INVALID, "plan shard (index, count) does not match the communicator (rank, size)");
+    if (p->device != cm->device) return fail(BFSM_ERR_INVALID, "plan and communicator live on different devices");
+    return BFSM_OK;
+}
+// this rank's partial Q: gain of its pair shard in physical space, minus the loss term on rank 0
+int sharded_partial(bfsm_plan *p, double *Q, const double *f, cudaStream_t st)
+{
+    int rc = do_gain_hat(p, p->qhat, f, st);
+    if (rc) return rc;
+    return do_finish(p, Q, p->qhat, f, st, /*with_loss=*/p->shard_index == 0);
+}
+} // namespace
+
+extern "C" int bfsm_collide_sharded(bfsm_plan *p, bfsm_comm *cm, double *Q_dev, const double *f_dev, void *stream)
+{
+    if (!Q_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    int rc = check_shard(p, cm);
+    if (rc) return rc;
+    NcclApi *api = nccl_api();
+    GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((rc = sharded_partial(p, Q_dev, f_dev, st))) return rc;
+    const size_t n = (size_t)p->N * p->N * p->N;
+    NCCL_TRY(api, api->AllReduce(Q_dev, Q_dev, n, ncclDouble, ncclSum, cm->comm, st));
+    return BFSM_OK;
+}
+
+// One host thread driving every rank (ncclCommInitAll): all local work is enqueued first, the
+// collectives are issued as one NCCL group.
+extern "C" int bfsm_collide_sharded_group(int n_ranks, bfsm_plan **plans, bfsm_comm **comms, double **Q_dev,
+                                          const double **f_dev, void **streams)
+{
+    if (n_ranks < 1 || !plans || !comms || !Q_dev || !f_dev) return fail(BFSM_ERR_INVALID, "bad argument");
+    NcclApi *api = nccl_api();
+    if (!api) return fail(BFSM_ERR_COMM, "NCCL (libnccl.so.2) could not be loaded");
+    for (int k = 0; k < n_ranks; ++k) {
+        int rc = check_shard(plans[k], comms[k]);
+        if (rc) return rc;
+        if (!Q_dev[k] || !f_dev[k]) return fail(BFSM_ERR_INVALID, "NULL buffer");
+        GuardDevice guard(plans[k]->device);
+        if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+        if ((rc = sharded_partial(plans[k], Q_dev[k], f_dev[k], streams ? (cudaStream_t)streams[k] : nullptr)))
+            return rc;
+    }
+    NCCL_TRY(api, api->GroupStart());
+    for (int k = 0; k < n_ranks; ++k) {
+        const size_t n = (size_t)plans[k]->N * plans[k]->N * plans[k]->N;
+        ncclResult_t r = api->AllReduce(Q_dev[k], Q_dev[k], n, ncclDouble, ncclSum, comms[k]->comm,
+                                        streams ? (cudaStream_t)streams[k] : nullptr);
+        if (r != ncclSuccess) {
+            api->GroupEnd();
+            return fail(BFSM_ERR_COMM, std::string("ncclAllReduce failed: ") + api->GetErrorString(r));
+        }
+    }
+    NCCL_TRY(api, api->GroupEnd());
+    return BFSM_OK;
+}
+
+// Pair-shard partial without the collective: for callers that own the exchange step (tests emulating
+// ranks on one GPU, other communication libraries).  Sum of Q_partial over all shards = Q(f,f).
+extern "C" int bfsm_collide_partial(bfsm_plan *p, double *Q_partial_dev, const double *f_dev, void *stream)
+{
+    if (!p || !Q_partial_dev || !f_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    return sharded_partial(p, Q_partial_dev, f_dev, (cudaStream_t)stream);
+}
+
+// ---- callers' helpers: integrator update and per-cell moments ---------------------------------
+extern "C" int bfsm_vec_axpby(int device, double *out_dev, double a, const double *x_dev, double b,
+                              const double *y_dev, unsigned long long n, void *stream)
+{
+    if (!out_dev || !x_dev || !y_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    GuardDevice guard(device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    if (n == 0) return BFSM_OK;
+    const int blocks = (int)std::min<unsigned long long>((n + 255) / 256, 148ull * 8);
+    k_axpby<<<blocks, 256, 0, (cudaStream_t)stream>>>(out_dev, a, x_dev, b, y_dev, (size_t)n);
+    CUDA_TRY(cudaGetLastError());
+    return BFSM_OK;
+}
+
+extern "C" int bfsm_moments(bfsm_plan *p, const double *g_dev, int n_cells, double *moments_dev, void *stream)
+{
+    if (!p || !g_dev || !moments_dev) return fail(BFSM_ERR_INVALID, "NULL argument");
+    if (n_cells < 0) return fail(BFSM_ERR_INVALID, "n_cells must be >= 0");
+    GuardDevice guard(p->device);
+    if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
+    if (n_cells == 0) return BFSM_OK;
+    k_moments<512><<<n_cells, 512, 0, (cudaStream_t)stream>>>(g_dev, p->N, p->L, moments_dev);
+    CUDA_TRY(cudaGetLastError());
     return BFSM_OK;
 }
 

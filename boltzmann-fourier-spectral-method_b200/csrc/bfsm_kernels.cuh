@@ -1046,33 +1046,41 @@ k_pencil_accum(const cplx *__restrict__ Ph, const cplx *__restrict__ twtab,
 }
 
 // Q = Re(IFFT_x H0) - Re(IFFT_x H1) * f                 (cpp:304-330)
-template <int N>
+// WITH_LOSS = false: Q = Re(IFFT_x H0) only -- the partial gain of one pair shard; the shards' Q are
+// summed by the all-reduce and exactly one rank adds the loss term (bfsm_collide_sharded).
+template <int N, bool WITH_LOSS>
 __global__ void __launch_bounds__(Geo<N>::B *TZ)
 k_pencil_final(const cplx *__restrict__ H, const cplx *__restrict__ twtab,
                const double *f, double *Q)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS;
     constexpr size_t N3 = (size_t)N * N * N;
-    __shared__ __align__(16) cplx sm[2][N * TZ];
+    __shared__ __align__(16) cplx sm[WITH_LOSS ? 2 : 1][N * TZ];
     const int tg = threadIdx.x;
     const int y = blockIdx.x / (N / TZ), zg = blockIdx.x % (N / TZ);
     const size_t off = (size_t)y * N + zg * TZ;
     cplx tw[A - 1];
     load_twiddles<N, +1>(tw, twtab, tg / TZ);
     x1_pass<N, +1>(sm[0], tw, tg, [&](int x, int z) { return H[off + (size_t)x * N * N + z]; });
-    x1_pass<N, +1>(sm[1], tw, tg, [&](int x, int z) { return H[N3 + off + (size_t)x * N * N + z]; });
+    if (WITH_LOSS)
+        x1_pass<N, +1>(sm[WITH_LOSS ? 1 : 0], tw, tg,
+                       [&](int x, int z) { return H[N3 + off + (size_t)x * N * N + z]; });
     __syncthreads();
 #pragma unroll
     for (int m = 0; m < UNITS; ++m) {
         cplx v0[B], v1[B];
         const int k1 = x2_unit<N, +1>(sm[0], tg, m, v0);
-        x2_unit<N, +1>(sm[1], tg, m, v1);
+        if (WITH_LOSS) x2_unit<N, +1>(sm[WITH_LOSS ? 1 : 0], tg, m, v1);
         const int z = (tg + m * B * TZ) % TZ;
 #pragma unroll
         for (int k2 = 0; k2 < B; ++k2) {
             const size_t idx = off + (size_t)(k1 + A * k2) * N * N + z;
-            const double fv = f[idx]; // read before the (possibly aliased) write below
-            Q[idx] = v0[k2].x - v1[k2].x * fv;
+            if (WITH_LOSS) {
+                const double fv = f[idx]; // read before the (possibly aliased) write below
+                Q[idx] = v0[k2].x - v1[k2].x * fv;
+            } else {
+                Q[idx] = v0[k2].x;
+            }
         }
     }
 }

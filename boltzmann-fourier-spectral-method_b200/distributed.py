@@ -30,6 +30,39 @@ def shard_cells(n_cells, rank, world_size):
     return shard_range(n_cells, rank, world_size)
 
 
+class NcclCommunicator:
+    """A bfsm_comm (include/bfsm_b200.h): an NCCL communicator owned by the C library, one rank per
+    process.  Rank 0 draws the NCCL unique id; the 128 bytes travel to the other ranks through the
+    already initialised torch.distributed group (any backend) -- torch is only the side channel."""
+
+    def __init__(self, device, group=None):
+        import ctypes
+        from . import _capi
+        lib = _capi.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = ctypes.create_string_buffer(_capi.BFSM_UNIQUE_ID_BYTES)
+        if rank == 0:
+            _capi.check(lib.bfsm_comm_unique_id(uid))
+        box = [uid.raw if rank == 0 else None]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0,
+                                   group=group)
+        self._lib = lib
+        self.handle = ctypes.c_void_p()
+        self.rank, self.world_size, self.device = rank, world, int(device)
+        _capi.check(lib.bfsm_comm_init_rank(ctypes.byref(self.handle), box[0], world, rank, self.device))
+
+    def close(self):
+        if self.handle:
+            self._lib.bfsm_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class PairShardedCollision:
     """Q(f,f) with the (r, sigma) pairs sharded over the ranks of `group`.
 
@@ -37,10 +70,13 @@ class PairShardedCollision:
     (for the CUDA path: BoltzmannOperatorB200(..., shard_index=rank, shard_count=world)).
     """
 
-    def __init__(self, local, grid_size, group=None):
+    def __init__(self, local, grid_size, group=None, comm=None):
         self.local = local
         self.grid_size = int(grid_size)
         self.group = group
+        #: NcclCommunicator: the whole step, collective included, runs inside the C library
+        #: (bfsm_collide_sharded); None: gain_hat / all_reduce through torch.distributed / finish
+        self.comm = comm
         self._qhat = None
 
     def _buffer(self, like):
@@ -49,6 +85,8 @@ class PairShardedCollision:
         return self._qhat
 
     def computeCollision(self, Q, f_in):
+        if self.comm is not None:
+            return self.local.collide_sharded(Q, f_in, self.comm)
         qhat = self._buffer(f_in)
         self.local.gain_hat(qhat, f_in)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:

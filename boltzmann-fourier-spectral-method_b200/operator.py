@@ -185,6 +185,71 @@ class BoltzmannOperatorB200:
             self._stream(stream), ms, cnt))
         return {name: (ms[i], cnt[i]) for i, name in enumerate(_capi.KCLASS_NAMES)}
 
+    # ------------------------------------------------------------------ streaming host buffers
+    def submit_host(self, Q, f_in, comm=None, n_cells=None, stream=None):
+        """Pipelined evaluation with HOST buffers (numpy arrays or CPU tensors, ideally pinned):
+        enqueues H2D copy, evaluation and D2H copy of this step and returns; the copies of neighbouring
+        steps overlap the kernels (bfsm_collide_host_async).  Q is valid after flush_host(), or once
+        two further steps have been submitted.  `comm`: NcclCommunicator for a sharded plan."""
+        self._require()
+        torch = _torch()
+        f_np = f_in.numpy() if isinstance(f_in, torch.Tensor) else np.asarray(f_in)
+        q_np = Q.numpy() if isinstance(Q, torch.Tensor) else Q
+        for a, name in ((f_np, "f_in"), (q_np, "Q")):
+            if not isinstance(a, np.ndarray) or a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                raise TypeError(f"{name} must be a C-contiguous float64 host array")
+        N = self.grid_size
+        if n_cells is None:
+            n_cells = f_np.size // N
+        if n_cells < 1 or f_np.size != n_cells * N or q_np.size != n_cells * N:
+            raise ValueError("f_in / Q size does not match n_cells * Nvx*Nvy*Nvz")
+        with torch.cuda.device(self.device):
+            _capi.check(self._lib.bfsm_collide_host_async(
+                self._plan, comm.handle if comm is not None else None, ctypes.c_void_p(q_np.ctypes.data),
+                ctypes.c_void_p(f_np.ctypes.data), int(n_cells), self._stream(stream)))
+
+    def flush_host(self):
+        """Wait for every step submitted with submit_host()."""
+        self._require()
+        _capi.check(self._lib.bfsm_collide_host_flush(self._plan))
+
+    # ------------------------------------------------------------------ diagnostics
+    def moments(self, g, n_cells=None, stream=None):
+        """Per-cell velocity moments of the grids in the CUDA tensor `g` (f or Q): a (n_cells, 5) CUDA
+        tensor of dv^3 sum_v g (1, vx, vy, vz, |v|^2/2).  For f: density, momentum, energy density; for
+        Q(f,f): the conservation defects (mass, momentum and energy of the collision term vanish)."""
+        self._require()
+        torch = _torch()
+        N = self.grid_size
+        if n_cells is None:
+            n_cells = g.numel() // N
+        self._check_dev(g, n_cells * N, "g")
+        out = torch.empty((n_cells, 5), dtype=torch.float64, device=g.device)
+        _capi.check(self._lib.bfsm_moments(self._plan, ctypes.c_void_p(g.data_ptr()), int(n_cells),
+                                           ctypes.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out
+
+    # ------------------------------------------------------------------ multi-GPU (collective in C)
+    def collide_partial(self, Q_partial, f_in, stream=None):
+        """Q_partial <- this pair shard's partial Q (shard 0 carries the loss term): the sum over all
+        shards is Q(f,f).  For callers that own the exchange step."""
+        self._require()
+        self._check_dev(f_in, self.grid_size, "f_in")
+        self._check_dev(Q_partial, self.grid_size, "Q_partial")
+        _capi.check(self._lib.bfsm_collide_partial(self._plan, ctypes.c_void_p(Q_partial.data_ptr()),
+                                                   ctypes.c_void_p(f_in.data_ptr()), self._stream(stream)))
+        return Q_partial
+
+    def collide_sharded(self, Q, f_in, comm, stream=None):
+        """Q <- Q(f_in, f_in) with the pair shards summed by ONE ncclAllReduce issued inside the C
+        library (bfsm_collide_sharded); `comm` is a `distributed.NcclCommunicator`."""
+        self._require()
+        self._check_dev(f_in, self.grid_size, "f_in")
+        self._check_dev(Q, self.grid_size, "Q")
+        _capi.check(self._lib.bfsm_collide_sharded(self._plan, comm.handle, ctypes.c_void_p(Q.data_ptr()),
+                                                   ctypes.c_void_p(f_in.data_ptr()), self._stream(stream)))
+        return Q
+
     # ------------------------------------------------------------------ multi-GPU halves
     def gain_hat(self, Qhat, f_in, stream=None):
         """Qhat (2*N doubles, complex interleaved) <- this shard's partial gain spectrum."""

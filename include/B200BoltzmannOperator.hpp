@@ -53,10 +53,21 @@ public:
     void setDevice(int dev) { device = dev; }
     void setHostPointers(bool on) { host_pointers = on; }
     void setStream(void *cuda_stream) { stream = cuda_stream; }
+    // Multi-GPU: this operator evaluates pair shard `index` of `count`; give it the
+    // rank's communicator (bfsm_comm_init_rank / bfsm_comm_init_all / bfsm_comm_adopt of an ncclComm_t)
+    // and computeCollision() ends with the one all-reduce, leaving Q(f,f) on every rank.  Operators of
+    // several GPUs driven by ONE host thread must be called through computeCollisionGroup().
     void setShard(int index, int count)
     {
         shard_index = index;
         shard_count = count;
+    }
+    void setCommunicator(bfsm_comm *c) { comm = c; }
+    // Tuning options (bfsm_plan_options); defaults otherwise.
+    void setOptions(const bfsm_plan_options &o)
+    {
+        options = o;
+        have_options = true;
     }
 
     void initialize() override
@@ -68,9 +79,10 @@ public:
         const std::vector<double> &sy = spherical_quadrature->gety();
         const std::vector<double> &sz = spherical_quadrature->getz();
         const std::vector<double> &w_s = spherical_quadrature->getWeights();
-        check(bfsm_plan_create(&plan, Nvx, Nvy, Nvz, (int)rho.size(), rho.data(), w_r.data(),
-                               (int)sx.size(), sx.data(), sy.data(), sz.data(), w_s.data(), gamma,
-                               b_gamma, L, device, shard_index, shard_count, 0u));
+        check(bfsm_plan_create_ex(&plan, Nvx, Nvy, Nvz, (int)rho.size(), rho.data(), w_r.data(),
+                                  (int)sx.size(), sx.data(), sy.data(), sz.data(), w_s.data(), gamma,
+                                  b_gamma, L, device, shard_index, shard_count, 0u,
+                                  have_options ? &options : nullptr));
     }
 
     std::string getBackendName() const override { return "B200"; }
@@ -78,12 +90,38 @@ public:
     void computeCollision(double *Q, const double *f_in) override
     {
         if (!plan) throw std::runtime_error("BoltzmannOperator<B200_Backend>: initialize() not called");
-        if (host_pointers) {
+        if (shard_count > 1) {
+            if (!comm) throw std::runtime_error("BoltzmannOperator<B200_Backend>: a sharded operator needs setCommunicator()");
+            if (host_pointers) throw std::runtime_error("BoltzmannOperator<B200_Backend>: sharded evaluation takes device pointers");
+            check(bfsm_collide_sharded(plan, comm, Q, f_in, stream));
+            check(bfsm_sync(plan, stream));
+        } else if (host_pointers) {
             check(bfsm_collide_host(plan, Q, f_in, 1, stream));
         } else {
             check(bfsm_collide(plan, Q, f_in, 1, stream));
             check(bfsm_sync(plan, stream)); // result valid on return, like the CUDA backend
         }
+    }
+
+    // One host thread, one sharded operator per GPU (communicators from bfsm_comm_init_all): every
+    // rank's kernels are enqueued, the all-reduces go out as one NCCL group, all streams are synchronised.
+    static void computeCollisionGroup(const std::vector<BoltzmannOperator<B200_Backend> *> &ops,
+                                      const std::vector<double *> &Q, const std::vector<const double *> &f_in)
+    {
+        const int n = (int)ops.size();
+        std::vector<bfsm_plan *> plans(n);
+        std::vector<bfsm_comm *> comms(n);
+        std::vector<double *> q(Q);
+        std::vector<const double *> f(f_in);
+        std::vector<void *> streams(n);
+        for (int k = 0; k < n; ++k) {
+            if (!ops[k]->plan || !ops[k]->comm) throw std::runtime_error("computeCollisionGroup: operator not ready");
+            plans[k] = ops[k]->plan;
+            comms[k] = ops[k]->comm;
+            streams[k] = ops[k]->stream;
+        }
+        check(bfsm_collide_sharded_group(n, plans.data(), comms.data(), q.data(), f.data(), streams.data()));
+        for (int k = 0; k < n; ++k) check(bfsm_sync(plans[k], streams[k]));
     }
 
     // Batch of independent cells (space-inhomogeneous use): n_cells consecutive grids.
@@ -124,6 +162,9 @@ private:
     bfsm_plan *plan = nullptr;
     int device = 0;
     int shard_index = 0, shard_count = 1;
+    bfsm_comm *comm = nullptr; // not owned
+    bfsm_plan_options options;
+    bool have_options = false;
     bool host_pointers = false;
     void *stream = nullptr;
 };

@@ -38,7 +38,8 @@ enum {
     BFSM_ERR_INVALID = 1,     /* bad argument (NULL pointer, non-positive size, bad shard) */
     BFSM_ERR_UNSUPPORTED = 2, /* grid shape not supported by this build */
     BFSM_ERR_CUDA = 3,        /* CUDA runtime error, message in bfsm_last_error() */
-    BFSM_ERR_NOMEM = 4
+    BFSM_ERR_NOMEM = 4,
+    BFSM_ERR_COMM = 5         /* NCCL missing or a collective failed, message in bfsm_last_error() */
 };
 
 /* plan flags */
@@ -47,6 +48,7 @@ enum {
                                 packed single transform + Nyquist-plane correction */
 
 typedef struct bfsm_plan bfsm_plan;
+typedef struct bfsm_comm bfsm_comm; /* NCCL communicator wrapper, see bfsm_comm_* below */
 
 int bfsm_version(void);
 const char *bfsm_last_error(void);
@@ -123,6 +125,19 @@ int bfsm_collide_host(bfsm_plan *plan, double *Q_host, const double *f_host, int
                       void *stream);
 
 /*
+ * Pipelined host-pointer evaluation for callers that stream many evaluations: returns as soon as step k
+ * is enqueued -- H2D copy of f on a copy stream, kernels on `stream`, D2H copy of Q on a second copy
+ * stream, two staging slots -- so that the copies of neighbouring steps run under the kernels.  The call
+ * blocks only until the step submitted TWO calls earlier has delivered its Q; bfsm_collide_host_flush()
+ * waits for everything outstanding.  Host buffers should be page-locked and must stay untouched until
+ * their step is complete.  With a sharded plan pass the rank's communicator (one cell per call, every
+ * rank submits the same sequence); NULL otherwise.
+ */
+int bfsm_collide_host_async(bfsm_plan *plan, bfsm_comm *comm_or_null, double *Q_host, const double *f_host,
+                            int n_cells, void *stream);
+int bfsm_collide_host_flush(bfsm_plan *plan);
+
+/*
  * Multi-GPU split of one evaluation (one cell).  Step 1 on every rank: this shard's partial
  * gain spectrum  Qhat_dev[2*N] (complex, re/im interleaved) = sum over the shard's pairs of
  * W_rs * beta1_r(|l|) * FFT3(Re(g1*g2))   (FFTWBoltzmannOperator.cpp:191-276 restricted to the
@@ -138,6 +153,34 @@ int bfsm_gain_hat(bfsm_plan *plan, double *Qhat_dev, const double *f_dev, void *
 int bfsm_finish(bfsm_plan *plan, double *Q_dev, const double *Qhat_dev, const double *f_dev,
                 void *stream);
 
+/*
+ * Pair-sharded evaluation with the collective under the ABI ("N_r x N_sigma pairs
+ * shard over 2/4/8 GPUs, followed by one NCCL allreduce").  A communicator wraps an ncclComm_t; NCCL is
+ * bound at run time (dlopen), so the library has no link-time NCCL dependency.
+ *
+ *   one process per GPU:  rank 0 calls bfsm_comm_unique_id() and sends the 128 bytes to the other ranks
+ *                         (any side channel); every rank calls bfsm_comm_init_rank();
+ *   one process, n GPUs:  bfsm_comm_init_all() (ncclCommInitAll), then bfsm_collide_sharded_group();
+ *   existing ncclComm_t:  bfsm_comm_adopt() (not destroyed by bfsm_comm_destroy).
+ *
+ * bfsm_collide_sharded: plan k of W (shard_index = k, shard_count = W = communicator size) evaluates its
+ * shard, transforms its partial gain spectrum back to physical space (linear, so the partial Q's add
+ * up), rank 0 subtracts the loss term, and ONE ncclAllReduce(sum) of N real doubles, in place in Q_dev,
+ * leaves Q(f,f) on every rank.  Asynchronous on `stream`.
+ */
+#define BFSM_UNIQUE_ID_BYTES 128
+int bfsm_comm_unique_id(unsigned char *id /* [BFSM_UNIQUE_ID_BYTES] */);
+int bfsm_comm_init_rank(bfsm_comm **out, const unsigned char *id, int n_ranks, int rank, int device);
+int bfsm_comm_init_all(bfsm_comm **comms /* [n_devices] */, int n_devices, const int *devices);
+int bfsm_comm_adopt(bfsm_comm **out, void *nccl_comm, int n_ranks, int rank, int device);
+int bfsm_comm_destroy(bfsm_comm *comm);
+int bfsm_collide_sharded(bfsm_plan *plan, bfsm_comm *comm, double *Q_dev, const double *f_dev, void *stream);
+int bfsm_collide_sharded_group(int n_ranks, bfsm_plan **plans, bfsm_comm **comms, double **Q_dev,
+                               const double **f_dev, void **streams /* may be NULL */);
+/* The shard's partial Q without the collective (sum over all shards = Q(f,f)); for callers that own the
+ * exchange step. */
+int bfsm_collide_partial(bfsm_plan *plan, double *Q_partial_dev, const double *f_dev, void *stream);
+
 /* cudaStreamSynchronize(stream) on the plan's device. */
 int bfsm_sync(bfsm_plan *plan, void *stream);
 
@@ -147,6 +190,19 @@ int bfsm_device_malloc(int device, void **ptr, unsigned long long bytes);
 int bfsm_device_free(int device, void *ptr);
 int bfsm_copy_to_device(int device, void *dst_dev, const void *src_host, unsigned long long bytes);
 int bfsm_copy_to_host(int device, void *dst_host, const void *src_dev, unsigned long long bytes);
+
+/*
+ * Callers' helpers (the steps either side of the path):
+ *   bfsm_vec_axpby  out = a x + b y on `n` device doubles (out may alias x or y): the stage update of an
+ *                   explicit time integrator, so that RK stages never leave the device;
+ *   bfsm_moments    per-cell velocity moments of `n_cells` consecutive grids g (f or Q):
+ *                   moments_dev[5 c .. 5 c + 4] = dv^3 sum_v g (1, vx, vy, vz, |v|^2/2) on the plan's
+ *                   grid v_i = -L + dv/2 + i dv (maxwell_bkw_fftw.cpp:62-71).  Of f: density, momentum,
+ *                   energy; of Q(f,f): the conservation defects (all five vanish analytically).
+ */
+int bfsm_vec_axpby(int device, double *out_dev, double a, const double *x_dev, double b, const double *y_dev,
+                   unsigned long long n, void *stream);
+int bfsm_moments(bfsm_plan *plan, const double *g_dev, int n_cells, double *moments_dev, void *stream);
 
 /* Introspection (used by bench.py for the roofline arithmetic and by tests). */
 typedef struct {

@@ -282,6 +282,33 @@ def test_batch_runs_with_fewer_lanes_when_lane_memory_is_short():
     assert op.info()["batch_lanes_used"] == 2
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partial_Q_of_the_pair_shards_adds_up(port_oracle, world):
+    """bfsm_collide_partial is what bfsm_collide_sharded feeds to its one ncclAllReduce: shard k's
+    partial gain in PHYSICAL space (shard 0 also carries the loss term).  Emulating `world` ranks on
+    one GPU, the sum of the partial Q's must be Q(f,f): against the unsharded plan and the oracle."""
+    Nv, n_r, n_s = 16, 5, 12
+    gl, sd = quadrature(n_r, n_s)
+    f = make_input("noise", Nv)
+    f_dev = torch.from_numpy(f).cuda().reshape(-1)
+    total = torch.zeros(Nv ** 3, dtype=torch.float64, device="cuda")
+    part = torch.empty_like(total)
+    for r in range(world):
+        op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
+                                     shard_index=r, shard_count=world)
+        op.initialize()
+        op.collide_partial(part, f_dev)
+        total += part
+        with pytest.raises(capi.BfsmError):
+            op(part, f_dev)                # a sharded plan cannot evaluate Q on its own
+        op.close()
+    torch.cuda.synchronize()
+    ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    assert rel_linf(total.cpu().numpy(), ref) <= REL_LINF_TOL
+    op_full, _, _ = make_operator(Nv, n_r, n_s)
+    assert rel_linf(total.cpu().numpy(), _eval(op_full, f)) <= 1e-14
+
+
 # ---------------------------------------------------------------- full BASELINE sizes
 FULL = [(64, 32, 192), (32, 16, 94)]
 
@@ -335,10 +362,102 @@ def test_cpp_driver_reproduces_known_answer():
         for key in ("L1 error", "L2 error", "Linf error"):
             if line.startswith(key):
                 vals[key] = float(line.split(":")[1])
+    assert "Moments of Q (mass, momentum x y z, energy):" in out.stdout
     assert abs(vals["L1 error"] - 1.54029638e-03) <= 1e-7 * 1.54029638e-03
     assert abs(vals["L2 error"] - 1.01189917e-04) <= 1e-7 * 1.01189917e-04
     assert abs(vals["Linf error"] - 4.25120273e-05) <= 1e-7 * 4.25120273e-05
     assert "Run statistics for B200" in out.stdout
+
+
+def _norms(text, header):
+    """L1 / L2 / Linf printed by the driver under `header`."""
+    lines = text.splitlines()
+    k = [i for i, l in enumerate(lines) if l.startswith(header)][0]
+    return [float(lines[k + 1 + j].split(":")[1]) for j in range(3)]
+
+
+def test_cpp_driver_time_integration_and_conservation():
+    """BASELINE config 3 from the C++ side: maxwell_bkw_b200 --t0 --tfinal --dt integrates with RK4 on
+    the device (bfsm_vec_axpby stage updates), reports the error against the exact BKW solution, and
+    the moments of Q / of f(tfinal) (bfsm_moments): mass, momentum and energy are conserved."""
+    exe = os.path.join(ROOT, "boltzmann-fourier-spectral-method_b200", "drivers", "build", "maxwell_bkw_b200")
+    designs = os.path.join(ROOT, "oracle", "_ref", "designs")
+    if not (os.path.exists(exe) and os.path.isdir(designs)):
+        pytest.skip("driver or design files not built")
+    out = subprocess.run([exe, "--Nv", "32", "--Nr", "16", "--Ns", "48", "--t0", "5.6", "--tfinal", "6.0",
+                          "--dt", "0.1", "--design-dir", designs], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert "RK4: 4 steps, 16 evaluations" in out.stdout
+    l1, l2, linf = _norms(out.stdout, "Error of f(tfinal) against the exact BKW solution")
+    assert linf < 5e-4 and l1 < 5e-3            # spectral + quadrature error of the 32^3 / 16 x 48 setup
+    mq = [float(v) for v in out.stdout.split("Moments of Q (mass, momentum x y z, energy):")[1].split()[:5]]
+    # the fast spectral method conserves mass / energy up to its quadrature + truncation error (the exact
+    # BKW dQ has zero moments); momentum vanishes by symmetry, to rounding
+    assert abs(mq[0]) < 1e-5 and max(abs(v) for v in mq[1:4]) < 1e-12 and abs(mq[4]) < 1e-3
+    mf = [float(v) for v in out.stdout.split("Moments of f(tfinal) (mass, momentum x y z, energy):")[1].split()[:5]]
+    assert abs(mf[0] - 1) < 1e-5 and max(abs(v) for v in mf[1:4]) < 1e-10 and abs(mf[4] - 1.5) < 1e-3
+
+
+def test_cpp_driver_inside_the_reference_hierarchy_matches_the_fftw_backend():
+    """oracle/_ref/maxwell_bkw_b200_ref is the same driver compiled against the REFERENCE's own
+    AbstractCollisionOperator / quadrature classes with its FFTW backend linked in: --backend both runs
+    Q and the RK4 loop through both backends in one process and prints their difference."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "maxwell_bkw_b200_ref")
+    designs = os.path.join(ROOT, "oracle", "_ref", "designs")
+    if not (os.path.exists(exe) and os.path.isdir(designs)):
+        pytest.skip("built only where /root/reference exists (make -C oracle driver)")
+    out = subprocess.run([exe, "--Nv", "16", "--Nr", "8", "--Ns", "12", "--backend", "both", "--t0", "5.6",
+                          "--tfinal", "5.8", "--dt", "0.1", "--design-dir", designs],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    dq = float(out.stdout.split("B200 vs FFTW: max|dQ|/max|Q| =")[1].split()[0])
+    df = float(out.stdout.split("B200 vs FFTW after integration: max|df|/max|f| =")[1].split()[0])
+    assert dq <= REL_LINF_TOL and df <= REL_LINF_TOL
+    a = _norms(out.stdout, "Error of f(tfinal) against the exact BKW solution:")
+    b = _norms(out.stdout, "Error of f(tfinal) against the exact BKW solution (FFTW backend)")
+    for x, y in zip(a, b):
+        assert abs(x - y) <= 0.01 * y                 # north star: BKW error within 1 % of the reference's
+
+
+def test_pipelined_host_entry_point_matches_the_blocking_one():
+    """bfsm_collide_host_async keeps two steps in flight (copies on their own streams); every step's Q
+    must equal what the blocking host entry point returns, bit for bit, including batches."""
+    Nv, n_r, n_s = 16, 4, 12
+    op, _, _ = make_operator(Nv, n_r, n_s)
+    steps = 5
+    fs = [torch.from_numpy(make_input("maxmix", Nv, seed=k).reshape(-1).copy()).pin_memory() for k in range(steps)]
+    qs = [torch.empty(Nv ** 3, dtype=torch.float64).pin_memory() for _ in range(steps)]
+    for k in range(steps):
+        op.submit_host(qs[k], fs[k])
+    op.flush_host()
+    for k in range(steps):
+        ref = np.empty(Nv ** 3)
+        op(ref, fs[k].numpy())
+        assert np.array_equal(qs[k].numpy(), ref)
+    fb = torch.cat(fs[:3]).pin_memory()
+    qb = torch.empty_like(fb).pin_memory()
+    op.submit_host(qb, fb, n_cells=3)
+    op.flush_host()
+    assert np.array_equal(qb.numpy(), np.concatenate([q.numpy() for q in qs[:3]]))
+
+
+def test_moments_match_numpy(port_oracle):
+    """bfsm_moments against a direct NumPy evaluation, for a batch of cells of f and of Q."""
+    Nv, n_r, n_s, cells = 16, 4, 12, 3
+    op, gl, sd = make_operator(Nv, n_r, n_s)
+    fs = np.stack([make_input("maxmix", Nv, seed=c) for c in range(cells)])
+    f_dev = torch.from_numpy(fs).cuda().reshape(-1)
+    q_dev = torch.empty_like(f_dev)
+    op(q_dev, f_dev, n_cells=cells)
+    v, dv = inp.velocity_axis(Nv)
+    vx, vy, vz = np.meshgrid(v, v, v, indexing="ij")
+    basis = [np.ones_like(vx), vx, vy, vz, 0.5 * (vx ** 2 + vy ** 2 + vz ** 2)]
+    for dev, host in ((f_dev, fs), (q_dev, q_dev.cpu().numpy().reshape(cells, Nv, Nv, Nv))):
+        m = op.moments(dev).cpu().numpy()
+        ref = np.array([[(g * b).sum() * dv ** 3 for b in basis] for g in host])
+        assert np.abs(m - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    mq, mf = op.moments(q_dev).cpu().numpy(), op.moments(f_dev).cpu().numpy()
+    assert np.abs(mq[:, 0]).max() < 1e-2 * np.abs(mf[:, 0]).max()   # mass defect of Q: discretisation level
 
 
 def test_bkw_time_integration_matches_oracle_driven_integrator(port_oracle):

@@ -39,6 +39,23 @@ def test_port_matches_reference_golden_vectors(port_oracle, Nv, n_r, n_s, kind):
 
 
 @pytest.mark.parametrize("kind", ["maxmix", "noise"])
+def test_port_matches_reference_with_the_full_192_point_design(port_oracle, kind):
+    """One more link of the chain reference -> port -> GPU at the flagship size: the C port against the
+    UNMODIFIED reference operator at 64^3 with ALL 192 directions of ss019.192 and one radius (the
+    reference's six batch arrays need 4.8 GB there; the full 32-radius list would need 154.6 GB, which
+    is why the flagship golden itself, port_q_cfg4.npz, has to come from the port)."""
+    Nv, n_r, n_s = 64, 1, 192
+    G = np.load(os.path.join(GOLDEN, "reference_q_64cubed.npz"))
+    gl, sd = quadrature(n_r, n_s)
+    Q = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), make_input(kind, Nv)).reshape(Nv, Nv, Nv)
+    key, st = f"Nv{Nv}_r{n_r}_s{n_s}_{kind}", int(G["stride"])
+    qmax = float(G[key + "_max"])
+    assert np.abs(Q[::st, ::st, ::st] - G[key + "_Qsub"]).max() / qmax < ORACLE_TOL
+    assert np.abs(Q.sum(axis=(1, 2)) - G[key + "_plane_sum"]).max() / (qmax * Nv * Nv) < ORACLE_TOL
+    assert np.abs((Q * Q).sum(axis=(1, 2)) - G[key + "_plane_sumsq"]).max() / (qmax ** 2 * Nv * Nv) < ORACLE_TOL
+
+
+@pytest.mark.parametrize("kind", ["maxmix", "noise"])
 def test_port_matches_reference_at_64_cubed(port_oracle, kind):
     """64^3 is where the pipelined plane kernel runs; the GPU parity tests there check against the C
     port, so the port itself is pinned at that size against the UNMODIFIED reference operator:
