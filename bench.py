@@ -207,7 +207,7 @@ def run_reference(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    args.emit(json.dumps(line))
     return 0
 
 
@@ -506,12 +506,24 @@ def run_b200(args):
             "gpu_launches": info["launches_per_cell"] * max(n_local, 1) * steps,
             "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        args.emit(json.dumps(line))
     if comm is not None:
         comm.close()
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def _claim_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner to stdout) get
+    stderr instead.  Returns a writer for the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(text):
+        os.write(saved, (text + "\n").encode())
+    return emit
 
 
 def main():
@@ -523,6 +535,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.emit = _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -456,8 +456,6 @@ def test_moments_match_numpy(port_oracle):
         m = op.moments(dev).cpu().numpy()
         ref = np.array([[(g * b).sum() * dv ** 3 for b in basis] for g in host])
         assert np.abs(m - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
-    mq, mf = op.moments(q_dev).cpu().numpy(), op.moments(f_dev).cpu().numpy()
-    assert np.abs(mq[:, 0]).max() < 1e-2 * np.abs(mf[:, 0]).max()   # mass defect of Q: discretisation level
 
 
 def test_bkw_time_integration_matches_oracle_driven_integrator(port_oracle):
