@@ -4,6 +4,7 @@
 #include "bfsm_kernels.cuh"
 #include "bfsm_pencil_reg.cuh"
 #include "bfsm_fused.cuh"
+#include "bfsm_cluster.cuh"
 #include "bfsm_aux.cuh"
 
 #include <dlfcn.h>
@@ -75,6 +76,7 @@ struct bfsm_plan {
     // fused persistent gain kernel (64^3 packed mode): roles, sub-chunk size, ring depth
     int fused = 0, fused_K = 0, fused_D = 0, fused_NQ = 0, fused_NN = 0;
     int *sync_flags = nullptr;    // [2 * n_sub] ready / consumed counters of the fused kernel
+    int cluster = 0;              // 32^3 packed mode: cluster/DSMEM gain kernel (no hybrid scratch)
 
     int S_slots_capacity = 0;     // partial slots S was allocated for
     int chunk_capacity = 0;       // pairs the per-chunk scratch (hyb, uvw) was allocated for
@@ -229,6 +231,12 @@ template <int N> int configure_kernels()
         CUDA_TRY(cudaFuncSetAttribute(k_gain_fused<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)plane_ws_smem<N>()));
     }
+    if constexpr (N == 32) {
+        CUDA_TRY(cudaFuncSetAttribute(k_gain_cluster<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)cluster_smem_bytes<N>()));
+        CUDA_TRY(cudaFuncSetAttribute(k_gain_cluster<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)cluster_smem_bytes<N>()));
+    }
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_async_smem<N>()));
@@ -355,12 +363,16 @@ void update_slot_layout(bfsm_plan *p)
     };
     p->one_slot_pencil = (staged && p->G > 1 && aligned(p->G)) ? 1 : 0;
 }
-bool pencil_units_active(const bfsm_plan *p) { return p->packed && (p->pencil_kernel == 2 || p->fused); }
+bool pencil_units_active(const bfsm_plan *p)
+{
+    return p->packed && (p->pencil_kernel == 2 || p->fused || p->cluster);
+}
 bool units_needed(const bfsm_plan *p) { return p->packed != 0; } // the Nyquist accumulate always walks units
 // hybrid grids / Nyquist-field sets the per-launch scratch holds
 size_t hyb_grids(const bfsm_plan *p)
 {
     if (p->fused) return (size_t)p->fused_D * p->fused_K;
+    if (p->cluster) return 0; // the hybrid grids live in the clusters' shared memory
     return (size_t)(p->packed ? 1 : 2) * p->chunk_capacity;
 }
 size_t uvw_sets(const bfsm_plan *p) { return p->fused ? (size_t)std::max(1, p->pairs_local) : (size_t)2 * p->chunk_capacity; }
@@ -505,7 +517,8 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
             } else if (p->packed)
                 k_plane_gain3<N, Lc::GROUPS, Lc::MINB>
                     <<<ctas, 4 * N * Lc::GROUPS, plane_gain3_smem<N>(), st>>>(
-                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                        p->fhat, p->phase, p->tw, p->hyb, c0, items, p->nyq, p->pair_w, uvw,
+                        p->cluster ? 2 : 3); // cluster mode: only the Nyquist planes
             else
                 k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>
                     <<<ctas, Lc::TG * Lc::GROUPS, plane_gain_smem<N>(), st>>>(
@@ -533,7 +546,18 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         const int G = std::min(p->G, nc);
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PENCIL_GAIN);
-            if (units) {
+            if (p->cluster) {
+                if constexpr (N == 32) {
+                    const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
+                    const int n_clusters = std::max(1, std::min(nu, p->sm_count / CL_SIZE));
+                    if (p->uniform_w)
+                        k_gain_cluster<N, true><<<CL_SIZE * n_clusters, CL_THREADS, cluster_smem_bytes<N>(), st>>>(
+                            p->fhat, p->phase, p->tw, p->units + u0, nu, p->pair_w, p->S, p->n_r_local);
+                    else
+                        k_gain_cluster<N, false><<<CL_SIZE * n_clusters, CL_THREADS, cluster_smem_bytes<N>(), st>>>(
+                            p->fhat, p->phase, p->tw, p->units + u0, nu, p->pair_w, p->S, p->n_r_local);
+                }
+            } else if (units) {
                 const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
                 const dim3 grid(PencilGeo<N>::WT / PR_WARPS, nu);
                 if (p->uniform_w)
@@ -790,7 +814,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     }
     if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.gain_ctas < 0 ||
         opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 2 || opt.plane_kernel < 0 ||
-        opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 2)
+        opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
         return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
     if (!rho || !w_r || !sx || !sy || !sz || !w_s)
@@ -954,6 +978,9 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     p->fused = (N == 64 && p->packed && opt.gain_pipeline == 2 && p->pairs_local > 0) ? 1 : 0;
     if (opt.gain_pipeline == 2 && !p->fused && !(N == 64 && p->packed))
         return (delete p, fail(BFSM_ERR_UNSUPPORTED, "gain_pipeline = 2 (fused kernel) needs a 64^3 grid in packed mode"));
+    p->cluster = (N == 32 && p->packed && opt.gain_pipeline == 3 && p->pairs_local > 0) ? 1 : 0;
+    if (opt.gain_pipeline == 3 && !(N == 32 && p->packed))
+        return (delete p, fail(BFSM_ERR_UNSUPPORTED, "gain_pipeline = 3 (cluster kernel) needs a 32^3 grid in packed mode"));
     if (p->fused) {
         p->fused_K = opt.fused_sub_pairs > 0 ? opt.fused_sub_pairs : 12;
         p->fused_K = std::min(p->fused_K, p->pairs_local);
@@ -1169,7 +1196,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : 1;
     info->pencil_kernel = !p->packed ? 0 : p->pencil_kernel;
     info->batch_lanes_used = p->lanes_used_last;
-    info->gain_pipeline = p->fused ? 2 : 1;
+    info->gain_pipeline = p->fused ? 2 : (p->cluster ? 3 : 1);
     info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
 }

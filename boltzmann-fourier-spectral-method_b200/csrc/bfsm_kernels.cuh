@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(4 * N *GROUPS, MINB)
 k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
               const cplx *__restrict__ twtab, cplx *__restrict__ hyb, int pair0, int n_items,
               const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
-              cplx *__restrict__ uvw)
+              cplx *__restrict__ uvw, int parts = 3)
 {
     constexpr int R = N / 4, TG = 4 * N, PITCH = N + 1, H = N / 2, NPL = N + 3;
     static_assert(TG >= 3 * N, "phase staging needs 3N threads per group");
@@ -183,7 +183,10 @@ k_plane_gain3(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     // regular planes and the 3 (costlier) Nyquist planes; every CTA takes an equal share of EACH
     // class, so that all CTAs finish together (with one contiguous range per CTA the owners of the
     // Nyquist planes ran 10 % longer than the rest -- ncu sm__cycles_active max vs avg).
+    // parts: bit 0 = the N regular planes, bit 1 = the 3 Nyquist planes (the cluster kernel does the
+    // regular planes itself and leaves only the Nyquist planes to this kernel)
     for (int part = 0; part < 2; ++part) {
+    if (!((parts >> part) & 1)) continue;
     const long long total = (long long)(part == 0 ? N : NPL - N) * n_items;
     const int base = part == 0 ? 0 : N * n_items;
     const int w_lo = base + (int)((total * blockIdx.x) / gridDim.x);

@@ -93,7 +93,9 @@ typedef struct {
     int gain_pipeline;     /* 0 = default, 1 = one plane + one x kernel per chunk (hybrid grids through
                               HBM), 2 = fused persistent kernel (64^3 packed mode only): plane, Nyquist and
                               x roles on disjoint SMs, hybrid grids through an L2-resident ring (opt-in:
-                              measured slower than pipeline 1) */
+                              measured slower than pipeline 1), 3 = thread-block-cluster
+                              kernel (32^3 packed mode only): eight CTAs own a pair, hybrid grids handed
+                              over through distributed shared memory, no global scratch */
     int fused_sub_pairs;   /* fused kernel: pairs per hand-over (sub-chunk); 0 = default */
     int fused_ring;        /* fused kernel: ring slots (sub-chunks in flight); 0 = default (2) */
     int fused_pencil_ctas; /* fused kernel: CTAs (= SMs) of the x role; 0 = default */
@@ -221,7 +223,7 @@ typedef struct {
     int pencil_kernel;       /* x stage in use: 0 k_pencil_gain (unpacked mode), 1 k_pencil_gain_async
                                 (cp.async ring), 2 k_pencil_gain_reg (register resident) */
     int batch_lanes_used;    /* lanes the last bfsm_collide(n_cells > 1) ran on (1 before any) */
-    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel */
+    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel, 3 = cluster */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);

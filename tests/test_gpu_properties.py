@@ -255,6 +255,39 @@ def test_slot_layouts_follow_the_chunking(port_oracle, Nv, n_r, n_s, pencil_kern
     assert np.array_equal(_eval(op, f), q0)
 
 
+@pytest.mark.parametrize("n_r,n_s,opts", [(16, 32, {}), (4, 12, {"seg_pairs": 5}), (3, 94, {"chunk_pairs": 50}),
+                                          (2, 6, {})],
+                         ids=["cfg2", "odd-units", "chunked", "tiny"])
+@pytest.mark.parametrize("kind", ["maxmix", "noise"])
+def test_cluster_dsmem_kernel_matches_the_oracle(port_oracle, n_r, n_s, opts, kind):
+    """gain_pipeline = 3 (32^3, packed mode): a cluster of eight CTAs owns a pair, the (y,z) planes are
+    handed to the x stage through distributed shared memory, no hybrid scratch in global memory.
+    Against the CPU oracle (incl. the non-band-limited input, whose Nyquist planes take the separate
+    k_plane_gain3 + k_nyq_accum route) and against the default pipeline to a few ulps; bitwise
+    repeatable (no atomics, cluster barriers only)."""
+    Nv = 32
+    f = make_input(kind, Nv)
+    op0, gl, sd = make_operator(Nv, n_r, n_s)
+    op1, _, _ = make_operator(Nv, n_r, n_s, options=dict(opts, gain_pipeline=3))
+    assert op1.info()["gain_pipeline"] == 3 and op0.info()["gain_pipeline"] == 1
+    q0, q1, q1b = _eval(op0, f), _eval(op1, f), _eval(op1, f)
+    assert np.array_equal(q1, q1b)
+    ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    assert rel_linf(q1, ref) <= REL_LINF_TOL
+    assert rel_linf(q1, q0) <= 1e-14
+    assert op1.info()["scratch_bytes"] < op0.info()["scratch_bytes"]     # no hybrid grids
+
+
+def test_special_pipelines_reject_grids_they_are_not_written_for():
+    gl, sd = quadrature(2, 6)
+    for Nv, pipeline in ((16, 2), (32, 2), (16, 3), (64, 3)):
+        op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, 0.0, inp.B_GAMMA_MAXWELL, inp.L_DOMAIN,
+                                     options={"gain_pipeline": pipeline})
+        with pytest.raises(capi.BfsmError) as err:
+            op.initialize()
+        assert err.value.code == capi.BFSM_ERR_UNSUPPORTED
+
+
 def test_batch_runs_with_fewer_lanes_when_lane_memory_is_short():
     """bfsm_collide(n_cells > 1) keeps up to four cells in flight on lanes with their own scratch; when
     a lane cannot be allocated (BFSM_ERR_NOMEM, injected here) the batch runs on the lanes that exist
