@@ -107,6 +107,7 @@ struct bfsm_plan {
     cplx *fhat = nullptr;  // [N^3]
     cplx *tmp = nullptr;   // [max(2, n_r_local)][N^3]  hybrid scratch of the single-shot stages
     cplx *hyb = nullptr;   // [(packed ? 1 : 2)*chunk][N^3]
+    CUtensorMap hyb_tmap;  // hyb as the 3-D tensor [pair*N + x][y][2 z] of doubles (TMA-filled x stage)
     double *S = nullptr;   // [x-stage slots + Nyquist slots][n_r_local][N^3]
     cplx *nyq = nullptr;   // [3][N][N] Nyquist planes of fhat (packed mode)
     cplx *uvw = nullptr;   // [2][chunk][3][N][N] (packed mode, double buffered)
@@ -134,6 +135,7 @@ struct bfsm_plan {
     struct Lane {
         cplx *fhat = nullptr, *tmp = nullptr, *hyb = nullptr, *nyq = nullptr, *uvw = nullptr,
              *qhat = nullptr;
+        CUtensorMap hyb_tmap;
         double *S = nullptr;
         int *sync_flags = nullptr;
         cudaStream_t main = nullptr, side = nullptr;
@@ -241,6 +243,12 @@ template <int N> int configure_kernels()
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_async_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pencil_async_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pencil_async_smem<N>()));
+    CUDA_TRY(cudaFuncSetAttribute(k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)pencil_async_smem<N>()));
     CUDA_TRY(cudaFuncSetAttribute(k_plane_gain<N, Lc::TG, Lc::GROUPS, Lc::MINB>,
@@ -357,7 +365,7 @@ int build_units(bfsm_plan *p, std::vector<int> &slots_of_r)
 
 void update_slot_layout(bfsm_plan *p)
 {
-    const bool staged = p->packed && p->pencil_kernel == 1 && !p->fused;
+    const bool staged = p->packed && (p->pencil_kernel == 1 || p->pencil_kernel == 3) && !p->fused && !p->cluster;
     auto aligned = [&](int groups) {
         return shares_start_at_radius_boundaries(p->pairs_local, p->pair_lo, p->n_dir, p->chunk, groups);
     };
@@ -566,14 +574,22 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                 else
                     k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
                         p->hyb, c0, p->units + u0, p->pair_w, p->S, p->n_r_local);
-            } else if (p->packed && p->one_slot_pencil)
+            } else if (p->packed && p->pencil_kernel == 3 && p->one_slot_pencil)
+                k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true, true>
+                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local, p->hyb_tmap);
+            else if (p->packed && p->pencil_kernel == 3)
+                k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, false, true>
+                    <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local, p->hyb_tmap);
+            else if (p->packed && p->one_slot_pencil)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB, true>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
-                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local, p->hyb_tmap);
             else if (p->packed)
                 k_pencil_gain_async<N, Lc::PG, Lc::PSTAGES, Lc::PMINB>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_async_smem<N>(), st>>>(
-                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local);
+                        p->hyb, p->tw, p->pair_r, p->pair_w, p->r_end, p->S, c0, nc, p->n_r_local, p->hyb_tmap);
             else
                 k_pencil_gain<N, Lc::PG, Lc::PMINB>
                     <<<dim3(TILES, G), Lc::PG * TGP, pencil_gain_smem<N>(), st>>>(
@@ -641,19 +657,51 @@ int do_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaSt
 int do_configure(bfsm_plan *p) { DISPATCH_N(p, configure_kernels<N_>()); }
 int do_launch_count(const bfsm_plan *p) { DISPATCH_N(p, launches_per_cell<N_>(p)); }
 
+// ---- TMA descriptor of a hybrid scratch buffer ----------------------------------------------
+// hyb[pair][x][y][z] (complex doubles) as a rank-3 tensor of doubles: dim0 = 2 N (z, re/im interleaved),
+// dim1 = N (y), dim2 = N * pairs (pair * N + x); box = one x-stage tile (2 TZ, 1, N).  The encoder is a
+// driver entry point fetched through the runtime, so the library does not link libcuda.
+int make_hyb_tmap(const bfsm_plan *p, const cplx *hyb, size_t grids, CUtensorMap *out)
+{
+    std::memset(out, 0, sizeof *out);
+    if (!(p->packed && p->pencil_kernel == 3) || grids == 0) return BFSM_OK;
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+        return fail(BFSM_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t N = (cuuint64_t)p->N;
+    const cuuint64_t dims[3] = {2 * N, N, N * (cuuint64_t)grids};
+    const cuuint64_t strides[2] = {N * sizeof(cplx), N * N * sizeof(cplx)};
+    const cuuint32_t box[3] = {2 * TZ, 1, (cuuint32_t)N};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = ((encode_fn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)hyb, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[96];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+        return fail(BFSM_ERR_CUDA, b);
+    }
+    return BFSM_OK;
+}
+
 // ---- batch lanes --------------------------------------------------------------------------
 void lane_save(bfsm_plan *p, int k)
 {
     bfsm_plan::Lane &L = p->lanes[k];
     L.fhat = p->fhat; L.tmp = p->tmp; L.hyb = p->hyb; L.nyq = p->nyq; L.uvw = p->uvw;
-    L.qhat = p->qhat; L.S = p->S; L.side = p->side; L.sync_flags = p->sync_flags;
+    L.qhat = p->qhat; L.S = p->S; L.side = p->side; L.sync_flags = p->sync_flags; L.hyb_tmap = p->hyb_tmap;
     for (int j = 0; j < 2; ++j) { L.ev_plane[j] = p->ev_plane[j]; L.ev_nyq[j] = p->ev_nyq[j]; }
 }
 void lane_activate(bfsm_plan *p, int k)
 {
     const bfsm_plan::Lane &L = p->lanes[k];
     p->fhat = L.fhat; p->tmp = L.tmp; p->hyb = L.hyb; p->nyq = L.nyq; p->uvw = L.uvw;
-    p->qhat = L.qhat; p->S = L.S; p->side = L.side; p->sync_flags = L.sync_flags;
+    p->qhat = L.qhat; p->S = L.S; p->side = L.side; p->sync_flags = L.sync_flags; p->hyb_tmap = L.hyb_tmap;
     for (int j = 0; j < 2; ++j) { p->ev_plane[j] = L.ev_plane[j]; p->ev_nyq[j] = L.ev_nyq[j]; }
 }
 void lane_free(bfsm_plan *p, int k)
@@ -736,6 +784,7 @@ int lane_alloc(bfsm_plan *p, int k)
     if ((rc = need((void **)&L.qhat, sizeof(cplx) * N3))) return give_up(rc);
     if ((rc = need((void **)&L.tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local)))) return give_up(rc);
     if ((rc = need((void **)&L.hyb, sizeof(cplx) * N3 * hyb_grids(p)))) return give_up(rc);
+    if ((rc = make_hyb_tmap(p, L.hyb, hyb_grids(p), &L.hyb_tmap))) return give_up(rc);
     if (p->fused && (rc = need((void **)&L.sync_flags, sizeof(int) * 2 * (size_t)std::max(1, fused_subs(p)))))
         return give_up(rc);
     if ((rc = need((void **)&L.S, sizeof(double) * N3 * (size_t)std::max(1, p->S_slots_capacity) * nr)))
@@ -813,7 +862,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
         opt = *opts;
     }
     if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.gain_ctas < 0 ||
-        opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 2 || opt.plane_kernel < 0 ||
+        opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 3 || opt.plane_kernel < 0 ||
         opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
         return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
@@ -963,9 +1012,11 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
         const int occ = (N == 64) ? 1 : (N == 32) ? 2 : 4;
         p->gy = opt.gain_ctas > 0 ? opt.gain_ctas : p->sm_count * occ;
     }
-    // x stage: at 64^3 both kernels are HBM bound and the staged one interferes less with the side-stream
-    // Nyquist accumulate (173 vs 170 evals/s); at 32^3 / 16^3 the register-resident one is 15 % faster
-    p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : (N == 64 ? 1 : 2);
+    // x stage: at 64^3 every variant is HBM bound; the staged one interferes less with the side-stream
+    // Nyquist accumulate (174 vs 170 evals/s) and its TMA-filled ring spends no LSU issue slots on the
+    // copies (bitwise equal to the LDGSTS fill, same speed); at 32^3 / 16^3 the register-resident kernel
+    // is 15 % faster (profiles/r02_ab64_tma.log, r02_ab32_tma.log)
+    p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : (N == 64 ? 3 : 2);
     p->plane_ws = (N == 64 && opt.plane_kernel != 1) ? 1 : 0;
     // work units of the register-resident x stage: a quarter of a radius' directions, at most 24 pairs
     p->seg_pairs = opt.seg_pairs > 0 ? opt.seg_pairs : std::max(1, std::min(24, (n_dir + 3) / 4));
@@ -1022,6 +1073,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * std::max(2, p->n_r_local))))
         return bail(rc);
     if ((rc = dev_alloc(p, (void **)&p->hyb, sizeof(cplx) * N3 * hyb_grids(p)))) return bail(rc);
+    if ((rc = make_hyb_tmap(p, p->hyb, hyb_grids(p), &p->hyb_tmap))) return bail(rc);
     if (p->fused &&
         (rc = dev_alloc(p, (void **)&p->sync_flags, sizeof(int) * 2 * (size_t)std::max(1, fused_subs(p)))))
         return bail(rc);
@@ -1169,6 +1221,7 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
         const size_t per = sizeof(cplx) * N3 * (p->packed ? 1 : 2);
         int rc = regrow((void **)&p->hyb, per * c, per * p->chunk_capacity);
         if (rc) return rc;
+        if ((rc = make_hyb_tmap(p, p->hyb, (size_t)(p->packed ? 1 : 2) * c, &p->hyb_tmap))) return rc;
         if (p->packed) {
             const size_t pern = sizeof(cplx) * 2 * 3 * N * N;
             rc = regrow((void **)&p->uvw, pern * c, pern * p->chunk_capacity);

@@ -17,6 +17,7 @@
 //
 // No cuFFT, no tensor cores: the whole path is fp64 SIMT (DFMA/DADD) + LDS/STS.
 #pragma once
+#include <cuda.h> // CUtensorMap (type only; the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 
 namespace bfsm {
@@ -328,6 +329,55 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int KEEP> __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(KEEP) : "memory");
+}
+
+// ---- bulk asynchronous copies (TMA, SASS: UBLKCP) completing on an mbarrier ---------------------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}" ::"r"(a), "r"(parity) : "memory");
+}
+// `bytes` (a multiple of 16) from global to shared memory, completion counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, unsigned long long *bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(d), "l"(gmem_src), "r"(bytes), "r"(b) : "memory");
+}
+// One TMA tensor copy: the box at coordinates (c0, c1, c2) of the 3-D tensor map -> shared memory
+// (SASS: UTMALDG), completion counted on `bar`.
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const void *tmap, int c0, int c1, int c2,
+                                            unsigned long long *bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(d), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(b) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy ones
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 __device__ __forceinline__ void group_sync(int id, int nthreads)

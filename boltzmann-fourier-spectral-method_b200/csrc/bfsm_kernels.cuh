@@ -786,32 +786,45 @@ k_pencil_gain(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
 
 // ---------------------------------------------------------------------------------------
 // k_pencil_gain_async (packed mode): same work split and flush as k_pencil_gain, but each group
-// streams its tiles through a STAGES-deep ring of shared-memory slots filled by cp.async
-// (LDGSTS), so the global loads of the next pairs are in flight while the current pair is
-// transformed.  Per pair and group: wait for the oldest slot, x pass 1 in place, x pass 2,
-// acc += w (Re^2 - Im^2); two group barriers per pair.
+// streams its tiles through a STAGES-deep ring of shared-memory slots, so the global loads of the
+// next pairs are in flight while the current pair is transformed.  Per pair and group: wait for
+// the oldest slot, x pass 1 in place, x pass 2, acc += w (Re^2 - Im^2); two group barriers per pair.
+//
+// TMA = true: the ring is filled by the TMA unit -- a tile is the box (TZ z, 1 y, N x) of the hybrid
+// scratch seen as the 3-D tensor [pair*N + x][y][z] (8 KiB, rows of 128 contiguous bytes N^2 elements
+// apart); ONE thread of the group issues ONE cp.async.bulk.tensor (SASS UTMALDG) per tile and the
+// slot's mbarrier counts the bytes in -- no LSU issue slots and no address arithmetic for the copy.
+// TMA = false (default): cp.async (LDGSTS) fill, 8 copies per thread and tile.  Measured at 64^3 the
+// x stage is HBM bound either way (profiles/r02_ab64_tma.log).
 // ---------------------------------------------------------------------------------------
 // ONE_SLOT: every CTA row gy accumulates into partial slot 0 -- legal when the gy shares of the chunk
 // start at radius boundaries (then no two CTAs touch the same (radius, tile)); the host checks that.
-template <int N, int PG, int STAGES, int MINB, bool ONE_SLOT = false>
+template <int N, int PG, int STAGES, int MINB, bool ONE_SLOT = false, bool BULK = false>
 __global__ void __launch_bounds__(PG *Geo<N>::B *TZ, MINB)
 k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab,
                     const int *__restrict__ pair_r, const double *__restrict__ pair_w,
                     const int *__restrict__ r_end, double *__restrict__ S, int pair0,
-                    int n_pairs_chunk, int n_r_local)
+                    int n_pairs_chunk, int n_r_local, const __grid_constant__ CUtensorMap tmap)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B;
     constexpr int TGP = B * TZ, UNITS = X2<N>::UNITS, TILE = N * TZ;
-    constexpr int CP_PER_THREAD = TILE / TGP; // 16-byte copies per thread and tile
+    constexpr int CP_PER_THREAD = TILE / TGP; // 16-byte copies per thread and tile (LDGSTS fill)
     constexpr size_t N3 = (size_t)N * N * N;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    cplx(*ring)[STAGES][TILE] = reinterpret_cast<cplx(*)[STAGES][TILE]>(smem_raw); // [PG][STAGES][TILE]
+    extern __shared__ __align__(128) unsigned char smem_ring[]; // TMA destinations: 128-byte aligned
+    cplx(*ring)[STAGES][TILE] = reinterpret_cast<cplx(*)[STAGES][TILE]>(smem_ring); // [PG][STAGES][TILE]
+    __shared__ __align__(8) unsigned long long full[PG][STAGES]; // TMA: "tile landed" barriers
 
     const int g = threadIdx.x / TGP, tg = threadIdx.x % TGP;
     const int y = blockIdx.x / (N / TZ), zg = blockIdx.x % (N / TZ);
     const int G = gridDim.y;
     const int lo = (int)(((long long)n_pairs_chunk * blockIdx.y) / G);
     const int hi = (int)(((long long)n_pairs_chunk * (blockIdx.y + 1)) / G);
+
+    if (BULK) {
+        if (threadIdx.x < PG * STAGES) mbar_init(&full[0][0] + threadIdx.x, 1);
+        mbar_init_fence();
+        __syncthreads();
+    }
 
     cplx tw[A - 1];
     load_twiddles<N, +1>(tw, twtab, tg / TZ);
@@ -823,16 +836,25 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
         for (int k2 = 0; k2 < B; ++k2) acc[m][k2] = 0.0;
 
     const size_t tile_off = (size_t)y * N + zg * TZ;
-    // tile element e = x*TZ + z  <->  global x*N*N + z; thread copies e = tg + c*TGP
+    // tile element e = x*TZ + z  <->  global x*N*N + z
     auto issue = [&](int q, int slot) {
         const cplx *src = hyb + (size_t)q * N3 + tile_off;
         cplx *dst = ring[g][slot];
+        if (BULK) {
+            if (tg == 0) {
+                // coordinates in doubles / rows: (2 z0, y, pair * N)
+                mbar_expect_tx(&full[g][slot], TILE * sizeof(cplx));
+                tma_load_3d(dst, &tmap, 2 * zg * TZ, y, q * N, &full[g][slot]);
+            }
+        } else {
 #pragma unroll
-        for (int c = 0; c < CP_PER_THREAD; ++c) {
-            const int e = tg + c * TGP;
-            cp_async16(dst + e, src + (size_t)(e / TZ) * N * N + (e % TZ));
+            for (int c = 0; c < CP_PER_THREAD; ++c) {
+                const int e = tg + c * TGP;
+                cp_async16(dst + e, src + (size_t)(e / TZ) * N * N + (e % TZ));
+            }
         }
     };
+    unsigned used = 0; // BULK: tiles consumed so far by this group (slot = used % STAGES, parity from used / STAGES)
 
     int p = lo;
     // the pair list is r-major, so the radius segments of [lo,hi) are consecutive radii: only the
@@ -847,19 +869,30 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
         if (seg_end < hi) r_end_cur = __ldg(&r_end[r + 1]); // consumed at the next segment
         // this group's pairs: q_n = p + g + n*PG
         const int n_mine = (seg_end - p - g + PG - 1) / PG;
+        // BULK: the ring slots are used round robin over the whole kernel (`used`), so that every
+        // barrier's phase parity is (use count / STAGES) & 1
+        const unsigned base = used;
 #pragma unroll
         for (int s0 = 0; s0 < STAGES - 1; ++s0) {
-            if (s0 < n_mine) issue(p + g + s0 * PG, s0);
-            cp_async_commit();
+            if (s0 < n_mine) issue(p + g + s0 * PG, BULK ? (base + s0) % STAGES : s0);
+            if (!BULK) cp_async_commit();
         }
         for (int n = 0; n < n_mine; ++n) {
             const int q = p + g + n * PG;
             const double w = __ldg(&pair_w[pair0 + q]); // in flight during the wait and x pass 1
-            cp_async_wait<STAGES - 2>();   // this thread's copies for pair n have landed
-            group_sync(1 + g, TGP);        // ... and everybody else's; slot (n-1) is free again
-            if (n + STAGES - 1 < n_mine) issue(q + (STAGES - 1) * PG, (n + STAGES - 1) % STAGES);
-            cp_async_commit();
-            cplx *sm = ring[g][n % STAGES];
+            const int slot = BULK ? (int)((base + n) % STAGES) : n % STAGES;
+            if (BULK) {
+                mbar_wait(&full[g][slot], ((base + n) / STAGES) & 1); // pair n has landed
+                fence_proxy_async();           // my generic writes to the slot freed below come first
+                group_sync(1 + g, TGP);        // everybody is done with pair n-1: its slot is free again
+            } else {
+                cp_async_wait<STAGES - 2>();   // this thread's copies for pair n have landed
+                group_sync(1 + g, TGP);        // ... and everybody else's; slot (n-1) is free again
+            }
+            if (n + STAGES - 1 < n_mine)
+                issue(q + (STAGES - 1) * PG, BULK ? (int)((base + n + STAGES - 1) % STAGES) : (n + STAGES - 1) % STAGES);
+            if (!BULK) cp_async_commit();
+            cplx *sm = ring[g][slot];
             x1_pass_inplace<N, +1>(sm, tw, tg);
             group_sync(1 + g, TGP);
 #pragma unroll
@@ -871,10 +904,12 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
                     acc[m][k2] += w * (v0[k2].x * v0[k2].x - v0[k2].y * v0[k2].y);
             }
         }
-        cp_async_wait<0>();
+        used += (unsigned)n_mine;
+        if (!BULK) cp_async_wait<0>();
         // flush this radius: fixed-order reduction over the PG groups
+        if (BULK) fence_proxy_async(); // the reduction buffer below aliases ring slots the TMA unit wrote
         __syncthreads();
-        double *red = reinterpret_cast<double *>(smem_raw); // PG*TILE doubles <= ring size
+        double *red = reinterpret_cast<double *>(smem_ring); // PG*TILE doubles <= ring size
 #pragma unroll
         for (int m = 0; m < UNITS; ++m)
 #pragma unroll
@@ -893,6 +928,7 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
             for (int gg = 0; gg < PG; ++gg) s += red[gg * TILE + src];
             Sr[(size_t)x * N * N + z] += s;
         }
+        if (BULK) fence_proxy_async(); // generic writes to `red` precede the next segment's bulk copies
         __syncthreads();
         p = seg_end;
         ++r;

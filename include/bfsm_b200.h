@@ -81,8 +81,10 @@ int bfsm_plan_create(bfsm_plan **out, int nvx, int nvy, int nvz, int n_r, const 
 typedef struct {
     int struct_size;       /* = sizeof(bfsm_plan_options), set by bfsm_plan_options_init */
     int chunk_pairs;       /* pairs per launch of the gain kernels; 0 = heuristic */
-    int pencil_kernel;     /* x stage (packed mode): 0 = default, 1 = staged through a cp.async ring in
-                              shared memory, 2 = register resident (no shared memory, LDG + SHFL) */
+    int pencil_kernel;     /* x stage (packed mode): 0 = default, 1 = staged through a shared-memory ring
+                              filled by cp.async (LDGSTS), 2 = register resident (no shared memory, LDG +
+                              SHFL), 3 = the staged kernel with the ring filled by the TMA unit (one
+                              cp.async.bulk.tensor per tile + mbarrier) */
     int seg_pairs;         /* pairs per work unit of the register-resident x stage and of the Nyquist
                               accumulate (one partial slot per unit of a radius); 0 = heuristic */
     int plane_kernel;      /* (y,z) stage (packed mode): 0 = default, 1 = k_plane_gain3 (every warp runs
@@ -221,7 +223,8 @@ typedef struct {
                                 1 k_plane_gain3, 2 k_plane_gain_ws (warp-specialised pipeline, 64^3) */
     int partial_slots;       /* partial-sum slots of S_r summed per evaluation */
     int pencil_kernel;       /* x stage in use: 0 k_pencil_gain (unpacked mode), 1 k_pencil_gain_async
-                                (cp.async ring), 2 k_pencil_gain_reg (register resident) */
+                                (LDGSTS-filled ring), 2 k_pencil_gain_reg (register resident), 3
+                                k_pencil_gain_async with a TMA-filled ring */
     int batch_lanes_used;    /* lanes the last bfsm_collide(n_cells > 1) ran on (1 before any) */
     int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel, 3 = cluster */
 } bfsm_plan_info;

@@ -202,6 +202,7 @@ def test_deterministic_and_chunk_independent():
 
 
 @pytest.mark.parametrize("knobs", [{"plane_kernel": 1}, {"pencil_kernel": 2}, {"pencil_kernel": 2, "plane_kernel": 1},
+                                   {"pencil_kernel": 1}, {"pencil_kernel": 1, "chunk_pairs": 5},
                                    {"seg_pairs": 5}, {"side_stream": 0}, {"chunk_pairs": 7},
                                    {"chunk_pairs": 7, "pencil_kernel": 2}, {"gain_pipeline": 2},
                                    {"gain_pipeline": 2, "fused_sub_pairs": 5, "fused_ring": 3}],
@@ -218,7 +219,7 @@ def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
     f = make_input("noise", Nv)
     op0, gl, sd = make_operator(Nv, n_r, n_s)
     assert op0.info()["plane_kernel"] == 2          # k_plane_gain_ws is the default at 64^3
-    assert op0.info()["pencil_kernel"] == 1         # k_pencil_gain_async is the default x stage at 64^3
+    assert op0.info()["pencil_kernel"] == 3         # the TMA-filled k_pencil_gain_async is the default at 64^3
     q0 = _eval(op0, f)
     op1, _, _ = make_operator(Nv, n_r, n_s, options=knobs)
     for key, val in knobs.items():
@@ -234,7 +235,7 @@ def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
 
 
 @pytest.mark.parametrize("Nv,n_r,n_s", [(32, 16, 32), (64, 4, 12), (16, 8, 6)])
-@pytest.mark.parametrize("pencil_kernel", [1, 2])
+@pytest.mark.parametrize("pencil_kernel", [1, 2, 3])
 def test_slot_layouts_follow_the_chunking(port_oracle, Nv, n_r, n_s, pencil_kernel):
     """Partial-sum slots: the staged x stage and the Nyquist accumulate share ONE slot each whenever
     every CTA row's share of every launch starts at a radius boundary, and fall back to one slot per
