@@ -12,6 +12,7 @@ BFSM_OK, BFSM_ERR_INVALID, BFSM_ERR_UNSUPPORTED, BFSM_ERR_CUDA, BFSM_ERR_NOMEM, 
 BFSM_UNIQUE_ID_BYTES = 128
 BFSM_FLAG_NO_FOLD = 1
 BFSM_FLAG_NO_PACK = 2
+BFSM_FLAG_GENERAL = 4
 
 #: every symbol include/bfsm_b200.h declares
 EXPORTS = (
@@ -37,6 +38,7 @@ class PlanInfo(ctypes.Structure):
         ("scratch_bytes", ctypes.c_longlong), ("plane_kernel", ctypes.c_int),
         ("partial_slots", ctypes.c_int), ("pencil_kernel", ctypes.c_int),
         ("batch_lanes_used", ctypes.c_int), ("gain_pipeline", ctypes.c_int),
+        ("ny", ctypes.c_int), ("nz", ctypes.c_int), ("general", ctypes.c_int),
     ]
 
 

@@ -14,20 +14,20 @@ __global__ void __launch_bounds__(256) k_axpby(double *out, double a, const doub
         out[i] = a * x[i] + b * y[i];
 }
 
-// One CTA per cell: m[cell] = dv^3 * sum_v g(v) * (1, vx, vy, vz, |v|^2 / 2) on the grid
-// v_i = -L + dv/2 + i dv (maxwell_bkw_fftw.cpp:62-71), summed in a fixed order (deterministic).
+// One CTA per cell: m[cell] = dvx dvy dvz * sum_v g(v) * (1, vx, vy, vz, |v|^2 / 2) on the grid
+// v_i = -L + dv/2 + i dv per axis (maxwell_bkw_fftw.cpp:62-71), summed in a fixed order (deterministic).
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) k_moments(const double *__restrict__ g, int N, double L,
-                                                     double *__restrict__ m)
+__global__ void __launch_bounds__(THREADS) k_moments(const double *__restrict__ g, int nx, int ny, int nz,
+                                                     double L, double *__restrict__ m)
 {
     __shared__ double red[5][THREADS];
-    const size_t N3 = (size_t)N * N * N;
-    const double dv = 2.0 * L / N;
+    const size_t N3 = (size_t)nx * ny * nz;
+    const double dx = 2.0 * L / nx, dy = 2.0 * L / ny, dz = 2.0 * L / nz;
     const double *gc = g + (size_t)blockIdx.x * N3;
     double s[5] = {0, 0, 0, 0, 0};
     for (size_t idx = threadIdx.x; idx < N3; idx += THREADS) {
-        const int k = (int)(idx % N), j = (int)((idx / N) % N), i = (int)(idx / ((size_t)N * N));
-        const double vx = -L + 0.5 * dv + i * dv, vy = -L + 0.5 * dv + j * dv, vz = -L + 0.5 * dv + k * dv;
+        const int k = (int)(idx % nz), j = (int)((idx / nz) % ny), i = (int)(idx / ((size_t)nz * ny));
+        const double vx = -L + 0.5 * dx + i * dx, vy = -L + 0.5 * dy + j * dy, vz = -L + 0.5 * dz + k * dz;
         const double v = gc[idx];
         s[0] += v;
         s[1] += v * vx;
@@ -44,7 +44,7 @@ __global__ void __launch_bounds__(THREADS) k_moments(const double *__restrict__ 
             for (int q = 0; q < 5; ++q) red[q][threadIdx.x] += red[q][threadIdx.x + h];
         __syncthreads();
     }
-    if (threadIdx.x < 5) m[(size_t)blockIdx.x * 5 + threadIdx.x] = red[threadIdx.x][0] * dv * dv * dv;
+    if (threadIdx.x < 5) m[(size_t)blockIdx.x * 5 + threadIdx.x] = red[threadIdx.x][0] * dx * dy * dz;
 }
 
 } // namespace bfsm

@@ -5,6 +5,7 @@
 #include "bfsm_pencil_reg.cuh"
 #include "bfsm_fused.cuh"
 #include "bfsm_cluster.cuh"
+#include "bfsm_general.cuh"
 #include "bfsm_aux.cuh"
 
 #include <dlfcn.h>
@@ -81,6 +82,9 @@ struct bfsm_plan {
     int S_slots_capacity = 0;     // partial slots S was allocated for
     int chunk_capacity = 0;       // pairs the per-chunk scratch (hyb, uvw) was allocated for
     bfsm_plan_options opt;
+    // general path (non-cubic / not 16-32-64 grids): per-axis sizes and twiddle tables
+    int general = 0, nx = 0, ny = 0, nz = 0;
+    cplx *gen_tw[3] = {nullptr, nullptr, nullptr};
     int n_dir = 0, pair_lo = 0; // pairs per radius; global index of this shard's first pair
     cudaStream_t side = nullptr;
     cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr};
@@ -158,6 +162,8 @@ struct bfsm_plan {
 };
 
 namespace {
+
+size_t grid_points(const bfsm_plan *p) { return (size_t)p->nx * p->ny * p->nz; }
 
 int dev_alloc(bfsm_plan *p, void **out, size_t bytes)
 {
@@ -395,7 +401,7 @@ int nyq_slots(const bfsm_plan *p) { return p->packed ? p->unit_slots : 0; } // o
 // (re)builds everything that depends on the chunk size: unit table, slot layout, S capacity
 int relayout(bfsm_plan *p)
 {
-    const size_t N3 = (size_t)p->N * p->N * p->N;
+    const size_t N3 = grid_points(p);
     if (units_needed(p)) {
         std::vector<int> slots_of_r;
         p->unit_slots = build_units(p, slots_of_r);
@@ -638,6 +644,67 @@ template <int N> int launches_per_cell(const bfsm_plan *p)
     return 2 + (p->packed ? 1 + 3 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
 }
 
+// ---- general path (bfsm_general.cuh) -------------------------------------------------------
+int gen_blocks(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
+
+// in-place 3-D transform of `n_arr` consecutive arrays
+template <int SIGN> int gen_fft3(bfsm_plan *p, cplx *data, int n_arr, cudaStream_t st)
+{
+    const int n[3] = {p->nx, p->ny, p->nz};
+    const long long inner[3] = {(long long)p->ny * p->nz, p->nz, 1};
+    const long long total = (long long)p->nx * p->ny * p->nz * n_arr;
+    for (int ax = 2; ax >= 0; --ax) {
+        const int len = n[ax];
+        int lg = -1;
+        if ((len & (len - 1)) == 0) { lg = 0; while ((1 << lg) < len) ++lg; }
+        const long long lines = total / len;
+        const size_t smem = sizeof(cplx) * GEN_TL * (len + 1) * (lg >= 0 ? 1 : 2);
+        k_gen_fft_axis<SIGN><<<(unsigned)((lines + GEN_TL - 1) / GEN_TL), 256, smem, st>>>(
+            data, len, inner[ax], lines, p->gen_tw[ax], lg);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BFSM_OK;
+}
+
+int gen_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f, cudaStream_t st)
+{
+    const size_t n = (size_t)p->nx * p->ny * p->nz;
+    int rc;
+    // fhat = FFT3(f) / N   (cpp:168-186; the 1/N of cpp:162 folded in)
+    k_gen_r2c<<<gen_blocks(n), 256, 0, st>>>(f, 1.0 / (double)n, p->fhat, n);
+    if ((rc = gen_fft3<-1>(p, p->fhat, 1, st))) return rc;
+    CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * n * std::max(1, p->n_r_local), st));
+    for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk) {
+        const int nc = std::min(p->chunk, p->pairs_local - c0);
+        k_gen_phase<<<gen_blocks(n * nc), 256, 0, st>>>(p->fhat, p->phase, c0, nc, p->nx, p->ny, p->nz, p->hyb);
+        if ((rc = gen_fft3<+1>(p, p->hyb, 2 * nc, st))) return rc;
+        k_gen_prod_acc<<<gen_blocks(n), 256, 0, st>>>(p->hyb, p->pair_r, p->pair_w, c0, nc, n, p->S);
+    }
+    // Qhat = sum_r coef_r(|l|^2) FFT3(S_r), radii in batches of the scratch capacity
+    const int cap = 2 * p->chunk;
+    if (p->n_r_local == 0) CUDA_TRY(cudaMemsetAsync(qhat_out, 0, sizeof(cplx) * n, st));
+    for (int r0 = 0; r0 < p->n_r_local; r0 += cap) {
+        const int na = std::min(cap, p->n_r_local - r0);
+        k_gen_real_batch<<<gen_blocks(n * na), 256, 0, st>>>(p->S + (size_t)r0 * n, p->hyb, n * na);
+        if ((rc = gen_fft3<-1>(p, p->hyb, na, st))) return rc;
+        k_gen_coef_acc<<<gen_blocks(n), 256, 0, st>>>(p->hyb, p->coef, p->M, r0, na, p->nx, p->ny, p->nz,
+                                                      r0 == 0 ? 1 : 0, qhat_out);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return BFSM_OK;
+}
+
+int gen_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st, bool with_loss)
+{
+    const size_t n = (size_t)p->nx * p->ny * p->nz;
+    k_gen_final_in<<<gen_blocks(n), 256, 0, st>>>(qhat, p->fhat, p->beta2, p->nx, p->ny, p->nz, p->tmp);
+    int rc = gen_fft3<+1>(p, p->tmp, with_loss ? 2 : 1, st);
+    if (rc) return rc;
+    k_gen_final_out<<<gen_blocks(n), 256, 0, st>>>(p->tmp, f, Q, n, with_loss ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    return BFSM_OK;
+}
+
 #define DISPATCH_N(p, CALL)                                           \
     switch ((p)->N) {                                                 \
     case 16: { constexpr int N_ = 16; return CALL; }                  \
@@ -648,14 +715,24 @@ template <int N> int launches_per_cell(const bfsm_plan *p)
 
 int do_gain_hat(bfsm_plan *p, cplx *qhat, const double *f, cudaStream_t st)
 {
+    if (p->general) return gen_gain_hat(p, qhat, f, st);
     DISPATCH_N(p, run_gain_hat<N_>(p, qhat, f, st));
 }
 int do_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaStream_t st, bool with_loss = true)
 {
+    if (p->general) return gen_finish(p, Q, qhat, f, st, with_loss);
     DISPATCH_N(p, run_finish<N_>(p, Q, qhat, f, st, with_loss));
 }
 int do_configure(bfsm_plan *p) { DISPATCH_N(p, configure_kernels<N_>()); }
-int do_launch_count(const bfsm_plan *p) { DISPATCH_N(p, launches_per_cell<N_>(p)); }
+int do_launch_count(const bfsm_plan *p)
+{
+    if (p->general) {
+        const int chunks = (p->pairs_local + p->chunk - 1) / std::max(1, p->chunk);
+        const int rb = (p->n_r_local + 2 * p->chunk - 1) / std::max(1, 2 * p->chunk);
+        return 4 + 5 * chunks + 5 * rb + 5;
+    }
+    DISPATCH_N(p, launches_per_cell<N_>(p));
+}
 
 // ---- TMA descriptor of a hybrid scratch buffer ----------------------------------------------
 // hyb[pair][x][y][z] (complex doubles) as a rank-3 tensor of doubles: dim0 = 2 N (z, re/im interleaved),
@@ -873,12 +950,17 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     if (!(L > 0.0)) return fail(BFSM_ERR_INVALID, "L must be positive");
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count)
         return fail(BFSM_ERR_INVALID, "shard_index/shard_count out of range");
-    if (nvx != nvy || nvy != nvz || (nvx != 16 && nvx != 32 && nvx != 64)) {
-        char b[160];
-        snprintf(b, sizeof b, "grid %dx%dx%d not supported: this build handles cubic 16/32/64", nvx,
-                 nvy, nvz);
-        return fail(BFSM_ERR_UNSUPPORTED, b);
-    }
+    // cubic 16 / 32 / 64: the tuned kernels.  Any other even sizes from 4 to 128 per axis (non-cubic,
+    // not a power of two, 128): the general path (bfsm_general.cuh).
+    const bool tuned = (nvx == nvy && nvy == nvz && (nvx == 16 || nvx == 32 || nvx == 64)) &&
+                       !(flags & BFSM_FLAG_GENERAL);
+    for (int n : {nvx, nvy, nvz})
+        if (n < 4 || n > GEN_MAXLEN || (n & 1)) {
+            char b[200];
+            snprintf(b, sizeof b, "grid %dx%dx%d not supported: every axis must be even and between 4 and %d "
+                     "(the mode tables of FFTWBoltzmannOperator.cpp:50-57 assume even sizes)", nvx, nvy, nvz, GEN_MAXLEN);
+            return fail(BFSM_ERR_UNSUPPORTED, b);
+        }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -890,6 +972,8 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
 
     bfsm_plan *p = new bfsm_plan;
     p->N = nvx;
+    p->nx = nvx; p->ny = nvy; p->nz = nvz;
+    p->general = tuned ? 0 : 1;
     p->n_r = n_r;
     p->n_s = n_s;
     p->device = device;
@@ -900,7 +984,9 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     p->shard_count = shard_count;
     p->packed = (flags & BFSM_FLAG_NO_PACK) ? 0 : 1;
     const int N = p->N;
-    const size_t N3 = (size_t)N * N * N;
+    const size_t N3 = (size_t)nvx * nvy * nvz;
+    const int nax[3] = {nvx, nvy, nvz};
+    const int PT = nvx + nvy + nvz; // entries of a pair's phase table [ex | ey | ez]
 
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
@@ -958,9 +1044,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     std::vector<int> h_pair_r(std::max(p->pairs_local, 1));
     std::vector<double> h_pair_w(std::max(p->pairs_local, 1));
     std::vector<int> h_r_end(std::max(p->n_r_local, 1), 0);
-    std::vector<cplx> h_phase((size_t)std::max(p->pairs_local, 1) * 3 * N);
-    std::vector<int> mode(N);
-    for (int t = 0; t < N; ++t) mode[t] = t < N / 2 ? t : t - N; // cpp:50-57
+    std::vector<cplx> h_phase((size_t)std::max(p->pairs_local, 1) * PT);
     for (int q = 0; q < p->pairs_local; ++q) {
         const int pair = lo + q;
         const int r = pair / n_dir, d = pair % n_dir, s = rep[d];
@@ -970,15 +1054,19 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
         // theta = -(pi/(2L)) * rho_r * (l . sigma)  (cpp:209-210), separable in the three axes
         const long double c = -(PI_L / (2.0L * (long double)L)) * (long double)rho[r];
         const double sig[3] = {sx[s], sy[s], sz[s]};
-        for (int ax = 0; ax < 3; ++ax)
-            for (int t = 0; t < N; ++t) {
-                const long double th = c * (long double)mode[t] * (long double)sig[ax];
-                h_phase[((size_t)q * 3 + ax) * N + t] = make_double2((double)cosl(th), (double)sinl(th));
+        size_t off = (size_t)q * PT;
+        for (int ax = 0; ax < 3; ++ax) {
+            for (int t = 0; t < nax[ax]; ++t) {
+                const int mode = t < nax[ax] / 2 ? t : t - nax[ax]; // cpp:50-57
+                const long double th = c * (long double)mode * (long double)sig[ax];
+                h_phase[off + t] = make_double2((double)cosl(th), (double)sinl(th));
             }
+            off += nax[ax];
+        }
     }
 
     // ---- beta1 / beta2 tables indexed by the integer |l|^2 (cpp:252-265, 281-299)
-    p->M = 3 * (N / 2) * (N / 2) + 1;
+    p->M = (nvx / 2) * (nvx / 2) + (nvy / 2) * (nvy / 2) + (nvz / 2) * (nvz / 2) + 1;
     const double fft_scale = 1.0 / (double)N3; // cpp:162
     std::vector<double> h_coef((size_t)std::max(p->n_r_local, 1) * p->M, 0.0);
     std::vector<double> h_beta2(p->M, 0.0);
@@ -999,6 +1087,55 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     for (int t = 0; t < N; ++t) {
         const long double a = 2.0L * PI_L * (long double)t / (long double)N;
         h_tw[t] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    if (p->general) {
+        // ---- general path: per-axis twiddle tables, plain scratch, nothing else
+        p->opt = opt;
+        p->packed = 0;
+        p->uniform_w = 0;
+        p->chunk = p->chunk_capacity = std::max(1, std::min(opt.chunk_pairs > 0 ? opt.chunk_pairs : 8,
+                                                             std::max(1, p->pairs_local)));
+        int rc = BFSM_OK;
+        auto bailg = [&](int code) {
+            std::string keep = g_err;
+            bfsm_plan_destroy(p);
+            g_err = keep;
+            return code;
+        };
+        for (int ax = 0; ax < 3; ++ax) {
+            std::vector<cplx> tw(nax[ax]);
+            for (int t = 0; t < nax[ax]; ++t) {
+                const long double a = 2.0L * PI_L * (long double)t / (long double)nax[ax];
+                tw[t] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+            if ((rc = upload(p, &p->gen_tw[ax], tw))) return bailg(rc);
+        }
+        if ((rc = upload(p, &p->phase, h_phase))) return bailg(rc);
+        if ((rc = upload(p, &p->pair_r, h_pair_r))) return bailg(rc);
+        if ((rc = upload(p, &p->pair_w, h_pair_w))) return bailg(rc);
+        if ((rc = upload(p, &p->r_end, h_r_end))) return bailg(rc);
+        if ((rc = upload(p, &p->coef, h_coef))) return bailg(rc);
+        if ((rc = upload(p, &p->beta2, h_beta2))) return bailg(rc);
+        if ((rc = dev_alloc(p, (void **)&p->fhat, sizeof(cplx) * N3))) return bailg(rc);
+        if ((rc = dev_alloc(p, (void **)&p->qhat, sizeof(cplx) * N3))) return bailg(rc);
+        if ((rc = dev_alloc(p, (void **)&p->tmp, sizeof(cplx) * N3 * 2))) return bailg(rc);
+        if ((rc = dev_alloc(p, (void **)&p->hyb, sizeof(cplx) * N3 * 2 * (size_t)p->chunk))) return bailg(rc);
+        {
+            const size_t bytes = sizeof(double) * N3 * std::max(1, p->n_r_local);
+            cudaError_t e = cudaMalloc((void **)&p->S, bytes);
+            if (e != cudaSuccess)
+                return bailg(fail(e == cudaErrorMemoryAllocation ? BFSM_ERR_NOMEM : BFSM_ERR_CUDA,
+                                  "cudaMalloc of the per-radius sums failed"));
+            p->scratch_bytes += (long long)bytes;
+            p->S_slots_capacity = 1;
+        }
+        p->n_lanes = 1;
+        CUDA_TRY(cudaFuncSetAttribute(k_gen_fft_axis<+1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(2 * sizeof(cplx) * GEN_TL * (GEN_MAXLEN + 1))));
+        CUDA_TRY(cudaFuncSetAttribute(k_gen_fft_axis<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(2 * sizeof(cplx) * GEN_TL * (GEN_MAXLEN + 1))));
+        *out = p;
+        return BFSM_OK;
     }
 
     // ---- launch geometry
@@ -1204,6 +1341,10 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
     int c = chunk_pairs > 0 ? chunk_pairs : dflt;
     c = std::min(c, std::max(1, p->pairs_local));
     if (p->fused) return BFSM_OK; // the fused kernel covers the shard in one launch; see fused_sub_pairs
+    if (p->general) { // plain scratch: any chunk up to the allocated capacity
+        p->chunk = std::max(1, std::min(chunk_pairs > 0 ? chunk_pairs : p->chunk_capacity, p->chunk_capacity));
+        return BFSM_OK;
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     lanes_free(p); // re-allocated lazily with the new chunk size
     if (c > p->chunk_capacity) {
@@ -1249,7 +1390,11 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : 1;
     info->pencil_kernel = !p->packed ? 0 : p->pencil_kernel;
     info->batch_lanes_used = p->lanes_used_last;
-    info->gain_pipeline = p->fused ? 2 : (p->cluster ? 3 : 1);
+    info->gain_pipeline = p->general ? 0 : (p->fused ? 2 : (p->cluster ? 3 : 1));
+    info->ny = p->ny;
+    info->nz = p->nz;
+    info->general = p->general;
+    if (p->general) info->plane_kernel = info->pencil_kernel = -1;
     info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
 }
@@ -1281,7 +1426,7 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
                     "bfsm_gain_hat + your own reduction)");
     GuardDevice guard(p->device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
-    const size_t N3 = (size_t)p->N * p->N * p->N;
+    const size_t N3 = grid_points(p);
     cudaStream_t st = (cudaStream_t)stream;
     p->lanes_used_last = 1;
     if (n_cells >= 2 && p->n_lanes >= 2 && !p->profiling) {
@@ -1323,7 +1468,7 @@ extern "C" int bfsm_collide_host(bfsm_plan *p, double *Q_host, const double *f_h
     if (n_cells == 0) return BFSM_OK;
     GuardDevice guard(p->device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
-    const size_t N3 = (size_t)p->N * p->N * p->N;
+    const size_t N3 = grid_points(p);
     const size_t bytes = sizeof(double) * N3 * (size_t)n_cells;
     if (p->stage_cells < (size_t)n_cells) {
         if (p->stage_f) cudaFree(p->stage_f);
@@ -1356,7 +1501,7 @@ extern "C" int bfsm_collide_host_async(bfsm_plan *p, bfsm_comm *cm, double *Q_ho
     GuardDevice guard(p->device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     bfsm_plan::HostPipe &hp = p->pipe;
-    const size_t N3 = (size_t)p->N * p->N * p->N;
+    const size_t N3 = grid_points(p);
     const size_t bytes = sizeof(double) * N3 * (size_t)n_cells;
     if (!hp.h2d) {
         CUDA_TRY(cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking));
@@ -1652,7 +1797,7 @@ extern "C" int bfsm_collide_sharded(bfsm_plan *p, bfsm_comm *cm, double *Q_dev, 
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     cudaStream_t st = (cudaStream_t)stream;
     if ((rc = sharded_partial(p, Q_dev, f_dev, st))) return rc;
-    const size_t n = (size_t)p->N * p->N * p->N;
+    const size_t n = grid_points(p);
     NCCL_TRY(api, api->AllReduce(Q_dev, Q_dev, n, ncclDouble, ncclSum, cm->comm, st));
     return BFSM_OK;
 }
@@ -1676,7 +1821,7 @@ extern "C" int bfsm_collide_sharded_group(int n_ranks, bfsm_plan **plans, bfsm_c
     }
     NCCL_TRY(api, api->GroupStart());
     for (int k = 0; k < n_ranks; ++k) {
-        const size_t n = (size_t)plans[k]->N * plans[k]->N * plans[k]->N;
+        const size_t n = grid_points(plans[k]);
         ncclResult_t r = api->AllReduce(Q_dev[k], Q_dev[k], n, ncclDouble, ncclSum, comms[k]->comm,
                                         streams ? (cudaStream_t)streams[k] : nullptr);
         if (r != ncclSuccess) {
@@ -1719,7 +1864,7 @@ extern "C" int bfsm_moments(bfsm_plan *p, const double *g_dev, int n_cells, doub
     GuardDevice guard(p->device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
     if (n_cells == 0) return BFSM_OK;
-    k_moments<512><<<n_cells, 512, 0, (cudaStream_t)stream>>>(g_dev, p->N, p->L, moments_dev);
+    k_moments<512><<<n_cells, 512, 0, (cudaStream_t)stream>>>(g_dev, p->nx, p->ny, p->nz, p->L, moments_dev);
     CUDA_TRY(cudaGetLastError());
     return BFSM_OK;
 }

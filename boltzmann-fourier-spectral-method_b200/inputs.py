@@ -35,17 +35,24 @@ def bkw(Nv, t=6.5):
     return np.ascontiguousarray(f), np.ascontiguousarray(Q)
 
 
+def _shape(Nv):
+    """Nv: one size (cubic grid) or a (Nvx, Nvy, Nvz) tuple."""
+    return (Nv, Nv, Nv) if np.isscalar(Nv) else tuple(int(n) for n in Nv)
+
+
 def maxmix(Nv, seed=1234):
-    """Sum of four Maxwellians with seeded random density / temperature / drift."""
+    """Sum of four Maxwellians with seeded random density / temperature / drift; `Nv` may be a
+    (Nvx, Nvy, Nvz) tuple (every axis spans the same [-L, L])."""
     rng = np.random.default_rng(seed)
-    v, _ = velocity_axis(Nv)
-    f = np.zeros((Nv, Nv, Nv))
+    nx, ny, nz = _shape(Nv)
+    vx, vy, vz = velocity_axis(nx)[0], velocity_axis(ny)[0], velocity_axis(nz)[0]
+    f = np.zeros((nx, ny, nz))
     for _ in range(4):
         rho = rng.uniform(0.5, 1.5)
         T = rng.uniform(0.5, 1.5)
         u = rng.uniform(-2, 2, size=3)
-        r_sq = ((v[:, None, None] - u[0]) ** 2 + (v[None, :, None] - u[1]) ** 2
-                + (v[None, None, :] - u[2]) ** 2)
+        r_sq = ((vx[:, None, None] - u[0]) ** 2 + (vy[None, :, None] - u[1]) ** 2
+                + (vz[None, None, :] - u[2]) ** 2)
         f += rho * (2 * pi * T) ** -1.5 * np.exp(-r_sq / (2 * T))
     return np.ascontiguousarray(f)
 
@@ -53,7 +60,7 @@ def maxmix(Nv, seed=1234):
 def noise(Nv, seed=12345):
     """i.i.d. U(0,1) samples: not band limited, exercises the Nyquist planes (parity only)."""
     rng = np.random.default_rng(seed)
-    return np.ascontiguousarray(rng.random((Nv, Nv, Nv)))
+    return np.ascontiguousarray(rng.random(_shape(Nv)))
 
 
 def error_norms(Q, Q_exact, Nv):

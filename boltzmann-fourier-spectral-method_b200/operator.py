@@ -24,7 +24,7 @@ def _torch():
 
 class BoltzmannOperatorB200:
     def __init__(self, gl_quadrature, spherical_quadrature, Nvx, Nvy, Nvz, gamma, b_gamma, L,
-                 device=None, shard_index=0, shard_count=1, fold=True, pack=True, options=None):
+                 device=None, shard_index=0, shard_count=1, fold=True, pack=True, options=None, general=False):
         # like the reference constructors: store arguments only
         self.gl_quadrature = gl_quadrature
         self.spherical_quadrature = spherical_quadrature
@@ -34,6 +34,8 @@ class BoltzmannOperatorB200:
         self.shard_index, self.shard_count = int(shard_index), int(shard_count)
         self.fold = bool(fold)
         self.pack = bool(pack)
+        #: force the general-grid path even on a cubic 16/32/64 grid (tests)
+        self.general = bool(general)
         #: dict of bfsm_plan_options fields (chunk_pairs, pencil_kernel, ...); None = defaults
         self.options = dict(options or {})
         self._plan = None
@@ -71,8 +73,8 @@ class BoltzmannOperatorB200:
             len(sx), sx.ctypes.data_as(dp), sy.ctypes.data_as(dp), sz.ctypes.data_as(dp),
             w_s.ctypes.data_as(dp), self.gamma, self.b_gamma, self.L, self.device,
             self.shard_index, self.shard_count,
-            (0 if self.fold else _capi.BFSM_FLAG_NO_FOLD) | (0 if self.pack else _capi.BFSM_FLAG_NO_PACK),
-            ctypes.byref(opts))
+            (0 if self.fold else _capi.BFSM_FLAG_NO_FOLD) | (0 if self.pack else _capi.BFSM_FLAG_NO_PACK)
+            | (_capi.BFSM_FLAG_GENERAL if self.general else 0), ctypes.byref(opts))
         _capi.check(rc)
         self._plan = plan
         self._lib = lib

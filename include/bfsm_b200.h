@@ -14,8 +14,10 @@
  *   - plain pointers and sizes only; every function returns 0 on success, a BFSM_ERR_* code
  *     otherwise, and never calls exit(); bfsm_last_error() returns the message (thread local).
  *   - grids are row-major (i*Nvy + j)*Nvz + k, z fastest, real fp64, N = Nvx*Nvy*Nvz values
- *     (FFTWBoltzmannOperator.cpp:173).  This release supports cubic grids Nvx=Nvy=Nvz in
- *     {16, 32, 64}; anything else is rejected with BFSM_ERR_UNSUPPORTED at plan creation.
+ *     (FFTWBoltzmannOperator.cpp:173).  Cubic grids Nvx=Nvy=Nvz in {16, 32, 64} run on the tuned
+ *     kernels; every other combination of even sizes from 4 to 128 per axis (non-cubic, 128, sizes
+ *     that are not powers of two) runs on a slower general path; odd or larger sizes are rejected
+ *     with BFSM_ERR_UNSUPPORTED at plan creation.
  *   - `*_dev` pointers are device pointers on the plan's device (the CUDA backend's convention,
  *     CUDABoltzmannOperator.cu:119-134); `*_host` pointers are host pointers (the FFTW backend's).
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Device-pointer
@@ -46,6 +48,7 @@ enum {
 #define BFSM_FLAG_NO_FOLD 1u /* transform every (r,sigma) pair even if the design is antipodal */
 #define BFSM_FLAG_NO_PACK 2u /* two 3-D transforms per pair (g1 and g2) instead of the Hermitian-
                                 packed single transform + Nyquist-plane correction */
+#define BFSM_FLAG_GENERAL 4u /* use the general-grid path even for a cubic 16/32/64 grid (tests) */
 
 typedef struct bfsm_plan bfsm_plan;
 typedef struct bfsm_comm bfsm_comm; /* NCCL communicator wrapper, see bfsm_comm_* below */
@@ -226,7 +229,10 @@ typedef struct {
                                 (LDGSTS-filled ring), 2 k_pencil_gain_reg (register resident), 3
                                 k_pencil_gain_async with a TMA-filled ring */
     int batch_lanes_used;    /* lanes the last bfsm_collide(n_cells > 1) ran on (1 before any) */
-    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel, 3 = cluster */
+    int gain_pipeline;       /* 1 = plane + x kernel per chunk, 2 = fused persistent kernel, 3 = cluster,
+                                0 = general-grid path */
+    int ny, nz;              /* points along y and z (`n` is the x size) */
+    int general;             /* 1 if the general-grid path (bfsm_general.cuh) serves this plan */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);

@@ -226,11 +226,13 @@ class ReferenceOperator:
         self.lib = lib
         if threads:
             lib.bfsm_ref_set_threads(ctypes.c_int(int(threads)))
-        self.shape = (Nv, Nv, Nv)
+        # Nv: one size, or (Nvx, Nvy, Nvz) -- the reference class takes three (FFTWBoltzmannOperator.hpp:30-36)
+        self.shape = (Nv, Nv, Nv) if np.isscalar(Nv) else tuple(int(n) for n in Nv)
         self.n_gl, self.n_sph = n_gl, n_sph
         with _quiet_stdout():
             self.h = lib.bfsm_ref_create(
-                ctypes.c_int(Nv), ctypes.c_int(Nv), ctypes.c_int(Nv), ctypes.c_int(n_gl),
+                ctypes.c_int(self.shape[0]), ctypes.c_int(self.shape[1]), ctypes.c_int(self.shape[2]),
+                ctypes.c_int(n_gl),
                 ctypes.c_double(a), ctypes.c_double(b), ctypes.c_int(n_sph), ctypes.c_double(gamma),
                 ctypes.c_double(b_gamma), ctypes.c_double(L))
         if not self.h:

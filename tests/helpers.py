@@ -36,8 +36,10 @@ def rel_linf(a, b):
 
 
 def make_operator(Nv, n_r, n_s, **kw):
+    """Nv: one size (cubic) or a (Nvx, Nvy, Nvz) tuple."""
     gl, sd = quadrature(n_r, n_s)
-    op = B.BoltzmannOperatorB200(gl, sd, Nv, Nv, Nv, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
+    nx, ny, nz = (Nv, Nv, Nv) if np.isscalar(Nv) else Nv
+    op = B.BoltzmannOperatorB200(gl, sd, nx, ny, nz, inp.GAMMA_MAXWELL, inp.B_GAMMA_MAXWELL,
                                  inp.L_DOMAIN, **kw)
     op.initialize()
     return op, gl, sd
