@@ -3,12 +3,13 @@
 
     python tools/summarise_ncu.py launches gpurun_out/launches_v11.csv profiles/r01_launches_bench_v11.csv
     python tools/summarise_ncu.py full gpurun_out/prof_plane_ws_v11.ncu-rep profiles/r01_ncu_full_k_plane_gain_ws_v11.txt \
-           [pairs_in_launch]
+           [pairs_in_launch [kernel-name regex, for a report that holds several kernels]]
 
 `launches` copies the per-launch duration list (gpu__time_duration.sum, --clock-control none) and
 prints/returns per-kernel shares; `full` extracts the metrics the roofline discussion uses from one
 `ncu --set full` capture (read with `ncu -i ... --page raw/source --csv`).  Both also refresh the
-matching entries of profiles/r01_ncu_summary.json, which bench.py reads for `roofline.traffic`.
+matching entries of profiles/r02_ncu_summary.json ($BFSM_NCU_SUMMARY), which bench.py reads for
+`roofline.traffic`.
 """
 import csv
 import json
@@ -18,7 +19,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SUMMARY = os.path.join(ROOT, "profiles", "r01_ncu_summary.json")
+SUMMARY = os.path.join(ROOT, "profiles", os.environ.get("BFSM_NCU_SUMMARY", "r02_ncu_summary.json"))
 AIDS = ("k_dfma_peak", "at::", "vectorized_elementwise", "elementwise_kernel")  # measurement aids
 
 
@@ -71,13 +72,16 @@ def launches(src, dst, command):
     print(json.dumps(kernels, indent=1))
 
 
-def ncu_csv(rep, page):
-    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+def ncu_csv(rep, page, kernel=None):
+    cmd = ["ncu", "-i", rep, "--page", page, "--csv"]
+    if kernel:
+        cmd += ["-k", "regex:" + kernel]   # reports that hold several kernels: pick one
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(out.splitlines()))
 
 
-def full(rep, dst, pairs):
-    raw = ncu_csv(rep, "raw")
+def full(rep, dst, pairs, kernel_filter=None):
+    raw = ncu_csv(rep, "raw", kernel_filter)
     hdr, vals = raw[0], raw[2]
     m = dict(zip(hdr, vals))
     kernel = short_name(m.get("Kernel Name", "?"))
@@ -131,7 +135,7 @@ def full(rep, dst, pairs):
                                          (fp64_thread_inst / f("smsp__cycles_elapsed.avg", f("sm__cycles_elapsed.avg"))))
                                for op in ("dadd", "dmul", "dfma")}
     # stall samples per code region (regions end at BAR / setmaxnreg / EXIT instructions)
-    src = ncu_csv(rep, "source")
+    src = ncu_csv(rep, "source", kernel_filter)
     sh = src[1]
     ix = {h: i for i, h in enumerate(sh)}
     cols = [h for h in sh if h.startswith("stall_") and "Not Issued" not in h]
@@ -182,4 +186,5 @@ if __name__ == "__main__":
             "ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
         launches(sys.argv[2], sys.argv[3], cmd)
     else:
-        full(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+        full(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0,
+             sys.argv[5] if len(sys.argv) > 5 else None)
