@@ -1146,7 +1146,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     p->chunk_capacity = p->chunk;
     p->G = (N == 64) ? Launch<64>::G : (N == 32) ? Launch<32>::G : Launch<16>::G;
     {
-        const int occ = (N == 64) ? 1 : (N == 32) ? 2 : 4;
+        const int occ = (N == 64) ? Launch<64>::MINB : (N == 32) ? Launch<32>::MINB : Launch<16>::MINB;
         p->gy = opt.gain_ctas > 0 ? opt.gain_ctas : p->sm_count * occ;
     }
     // x stage: at 64^3 every variant is HBM bound; the staged one interferes less with the side-stream

@@ -113,7 +113,9 @@ def full(rep, dst, pairs, kernel_filter=None):
     rec = {
         "capture": os.path.basename(rep),
         "pairs_in_launch": pairs,
-        "duration_us": round(f("gpu__time_duration.sum"), 2),
+        "duration_us": round(f("gpu__time_duration.sum") * {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0,
+                                                             "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6}
+                             .get(unit.get("gpu__time_duration.sum", "us"), 1.0), 2),
         "dram_bytes_read": scaled("dram__bytes_read.sum"),
         "dram_bytes_write": scaled("dram__bytes_write.sum"),
         "warp_instructions": f("smsp__inst_executed.sum"),
