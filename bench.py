@@ -259,8 +259,9 @@ def roofline_of(info, prof, Nv, value_units_per_s, cells_per_unit, capi, local_r
     bytes_plane = 16 * N3 * (arrays * pairs + n_launch) + (16 * 3 * Nv * Nv * pairs if info["packed"] else 0)
     bytes_pencil = 16 * N3 * (arrays * pairs) + 8 * N3 * n_launch
     fused = info["gain_pipeline"] == 2
-    plane_names = {0: "k_plane_gain", 1: "k_plane_gain3", 2: "k_plane_gain_ws"}
-    pencil_names = {0: "k_pencil_gain", 1: "k_pencil_gain_async", 2: "k_pencil_gain_reg"}
+    plane_names = {0: "k_plane_gain", 1: "k_plane_gain3", 2: "k_plane_gain_ws", 3: "k_plane_gain_r32",
+                   4: "k_plane_gain_r32"}
+    pencil_names = {0: "k_pencil_gain", 1: "k_pencil_gain_async", 2: "k_pencil_gain_reg", 3: "k_pencil_gain_async"}
     if fused:
         cls, kernel_name, bytes_cls = "plane_gain", "k_gain_fused", bytes_plane + bytes_pencil
     elif prof["plane_gain"][0] >= prof["pencil_gain"][0]:
@@ -370,7 +371,8 @@ def run_b200(args):
     info = op.info()
 
     f_host = torch.from_numpy(np.ascontiguousarray(f_np)).pin_memory()
-    q_host = [torch.empty(n_local * N3, dtype=torch.float64).pin_memory() for _ in range(2)]
+    depth = capi.BFSM_HOST_PIPE_DEPTH  # steps the pipelined host entry point keeps in flight
+    q_host = [torch.empty(n_local * N3, dtype=torch.float64).pin_memory() for _ in range(depth)]
     f_dev = f_host.to(dev)
     q_dev = torch.empty_like(f_dev)
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)
@@ -437,11 +439,11 @@ def run_b200(args):
     parity_dev = max_over_ranks(max(errs) if errs else -1.0)
 
     # ---- end to end through the public operator with HOST buffers: every step copies its input from
-    # pinned host memory and its result back; two steps in flight (bfsm_collide_host_async)
+    # pinned host memory and its result back; BFSM_HOST_PIPE_DEPTH steps in flight (bfsm_collide_host_async)
     def e2e_step(k):
         if n_local:
-            op.submit_host(q_host[k & 1], f_host, comm=comm, n_cells=n_local)
-    for k in range(2):
+            op.submit_host(q_host[k % depth], f_host, comm=comm, n_cells=n_local)
+    for k in range(depth):
         e2e_step(k)
     op.flush_host()
     barrier()
@@ -452,7 +454,7 @@ def run_b200(args):
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = units_per_step * steps / e2e_s
-    q_e2e = q_host[(steps - 1) & 1].numpy().reshape(max(n_local, 1), -1) if n_local else np.zeros((0, N3))
+    q_e2e = q_host[(steps - 1) % depth].numpy().reshape(max(n_local, 1), -1) if n_local else np.zeros((0, N3))
     errs = [golden_parity(args.workload, Nv, n_r, n_s, q_e2e[c], seeds[c]) for c in range(min(n_local, 8))]
     errs = [e for e in errs if e is not None]
     parity_e2e = max_over_ranks(max(errs) if errs else -1.0)
@@ -501,7 +503,7 @@ def run_b200(args):
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * N3 * n_local,
                     "d2h_bytes_per_step": 8 * N3 * n_local,
-                    "how": "op.submit_host per step (pinned host buffers, H2D + kernels + D2H, two steps in "
+                    "how": "op.submit_host per step (pinned host buffers, H2D + kernels + D2H, four steps in "
                            "flight), flush at the end; wall clock, max over ranks"},
             "gpu_launches": info["launches_per_cell"] * max(n_local, 1) * steps,
             "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libbfsm_b200.so")
 
 BFSM_OK, BFSM_ERR_INVALID, BFSM_ERR_UNSUPPORTED, BFSM_ERR_CUDA, BFSM_ERR_NOMEM, BFSM_ERR_COMM = range(6)
 BFSM_UNIQUE_ID_BYTES = 128
+BFSM_HOST_PIPE_DEPTH = 4  # steps bfsm_collide_host_async keeps in flight
 BFSM_FLAG_NO_FOLD = 1
 BFSM_FLAG_NO_PACK = 2
 BFSM_FLAG_GENERAL = 4

@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libbfsm_b200.so")
 SOURCES = ["bfsm_capi.cu"]
-HEADERS = ["bfsm_fft.cuh", "bfsm_kernels.cuh", "bfsm_pencil_reg.cuh", "bfsm_fused.cuh",
+HEADERS = ["bfsm_fft.cuh", "bfsm_kernels.cuh", "bfsm_pencil_reg.cuh", "bfsm_fused.cuh", "bfsm_plane_r32.cuh", "bfsm_tmem.cuh",
+           "bfsm_cluster.cuh", "bfsm_general.cuh", "bfsm_aux.cuh",
            os.path.join("..", "..", "include", "bfsm_b200.h")]
 
 NVCC_FLAGS = [

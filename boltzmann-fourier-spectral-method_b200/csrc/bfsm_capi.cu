@@ -3,6 +3,7 @@
 #include "../../include/bfsm_b200.h"
 #include "bfsm_kernels.cuh"
 #include "bfsm_pencil_reg.cuh"
+#include "bfsm_plane_r32.cuh"
 #include "bfsm_fused.cuh"
 #include "bfsm_cluster.cuh"
 #include "bfsm_general.cuh"
@@ -17,6 +18,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 using namespace bfsm;
@@ -61,6 +63,7 @@ struct bfsm_plan {
     int packed = 1;   // Hermitian packing: one 3-D transform per pair + Nyquist-plane correction
     int pencil_kernel = 2; // x stage (packed): 1 = staged cp.async ring, 2 = register resident (units)
     int plane_ws = 0;      // warp-specialised pipelined plane kernel (packed mode, N = 64)
+    int plane_r32 = 0;     // radix-32 two-stage plane kernel (packed mode, N = 64 or 32)
     int use_side = 1;      // run k_nyq_accum on an internal side stream (overlaps the pencil kernel)
     // Staged x stage and Nyquist accumulate: CTA row gy owns share gy of a chunk's pairs and, in general,
     // partial slot gy of S.  When every share of every launch starts at a radius boundary no two rows
@@ -102,6 +105,7 @@ struct bfsm_plan {
     cplx *tw = nullptr;       // [N] exp(+2 pi i t/N)
     cplx *phase = nullptr;    // [pairs_local][3][N]
     cplx *zpm = nullptr;      // [pairs_local][N]  (Re+Im, Re-Im) of the z phase (k_plane_gain_ws)
+    cplx *zpm_r32 = nullptr;  // same with the entries k = 3 mod 4 negated at N = 64 (k_plane_gain_r32)
     int *pair_r = nullptr;    // [pairs_local] local radius index
     double *pair_w = nullptr; // [pairs_local] spherical weight (x2 when folded)
     int *r_end = nullptr;     // [n_r_local] one past the last local pair of that radius
@@ -118,15 +122,17 @@ struct bfsm_plan {
     cplx *qhat = nullptr;  // [N^3]
     double *stage_f = nullptr, *stage_q = nullptr; // host-pointer entry point staging
     size_t stage_cells = 0;
-    // pipelined host-pointer entry point (bfsm_collide_host_async): two staging slots, copies on their
-    // own streams so that the H2D of step k+1 and the D2H of step k-1 run under the kernels of step k
+    // pipelined host-pointer entry point (bfsm_collide_host_async): BFSM_HOST_PIPE_DEPTH staging slots,
+    // copies on their own streams so that the H2D of later steps and the D2H of earlier ones run under
+    // the kernels of step k.  (Two slots were enough on one GPU; with a collective in every step the
+    // host-side jitter of ANY rank stalls all of them, and a deeper queue absorbs it.)
     struct HostPipe {
-        double *f[2] = {nullptr, nullptr}, *q[2] = {nullptr, nullptr};
+        static constexpr int DEPTH = BFSM_HOST_PIPE_DEPTH;
+        double *f[DEPTH] = {}, *q[DEPTH] = {};
         size_t cells = 0;
         cudaStream_t h2d = nullptr, d2h = nullptr;
-        cudaEvent_t in_done[2] = {nullptr, nullptr}, comp_done[2] = {nullptr, nullptr},
-                    out_done[2] = {nullptr, nullptr};
-        bool used[2] = {false, false};
+        cudaEvent_t in_done[DEPTH] = {}, comp_done[DEPTH] = {}, out_done[DEPTH] = {};
+        bool used[DEPTH] = {};
         unsigned long long submitted = 0;
     } pipe;
     std::vector<void *> allocs;
@@ -212,6 +218,23 @@ template <int N> size_t plane_gain3_smem()
                            (size_t)Launch<N>::GROUPS * 2 * 3 * N);
 }
 
+// radix-32 plane kernel: groups per CTA and CTAs per SM, with the fhat line in registers (TM = false,
+// 8 warps per SM at 255 registers) or in tensor memory (TM = true, 11-12 warps per SM at 168 registers)
+template <int N, bool TM> struct R32Launch;
+template <> struct R32Launch<64, false> { static constexpr int G = 1, MINB = 2; };
+template <> struct R32Launch<64, true> { static constexpr int G = 1, MINB = 3; };
+template <> struct R32Launch<32, false> { static constexpr int G = 8, MINB = 1; };
+template <> struct R32Launch<32, true> { static constexpr int G = 11, MINB = 1; };
+
+template <int N, bool TM> int configure_plane_r32()
+{
+    using Rl = R32Launch<N, TM>;
+    CUDA_TRY(cudaFuncSetAttribute(k_plane_gain_r32<N, Rl::G, Rl::MINB, TM>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)plane_r32_smem<N, Rl::G>()));
+    return BFSM_OK;
+}
+
 template <int N> size_t plane_ws_smem()
 {
     return sizeof(cplx) * ((size_t)3 * N * (N + 1) + (size_t)2 * 4 * N + (size_t)N);
@@ -238,6 +261,10 @@ template <int N> int configure_kernels()
                                       (int)plane_ws_smem<N>()));
         CUDA_TRY(cudaFuncSetAttribute(k_gain_fused<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)plane_ws_smem<N>()));
+    }
+    if constexpr (N == 64 || N == 32) {
+        if (int rc = configure_plane_r32<N, false>()) return rc;
+        if (int rc = configure_plane_r32<N, true>()) return rc;
     }
     if constexpr (N == 32) {
         CUDA_TRY(cudaFuncSetAttribute(k_gain_cluster<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -522,7 +549,21 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         int ctas = std::min(p->gy, std::max(1, (N * items) / Lc::GROUPS));
         {
             ProfSpan ps(p, st, BFSM_KCLASS_PLANE_GAIN);
-            if (N == 64 && p->packed && p->plane_ws) {
+            if (p->packed && p->plane_r32 && !p->cluster) {
+                if constexpr (N == 64 || N == 32) {
+                    auto launch = [&](auto tm) {
+                        constexpr bool TM = decltype(tm)::value;
+                        using Rl = R32Launch<N, TM>;
+                        const int groups = (N + 3) * items; // never more groups than list entries
+                        const int grid = std::max(1, std::min(p->sm_count * Rl::MINB, (groups + Rl::G - 1) / Rl::G));
+                        k_plane_gain_r32<N, Rl::G, Rl::MINB, TM>
+                            <<<grid, Rl::G * R32Geo<N>::GT, plane_r32_smem<N, Rl::G>(), st>>>(
+                                p->fhat, p->phase, p->zpm_r32, p->hyb, c0, items, p->nyq, p->pair_w, uvw);
+                    };
+                    if (p->plane_r32 == 2) launch(std::true_type{});
+                    else launch(std::false_type{});
+                }
+            } else if (N == 64 && p->packed && p->plane_ws) {
                 if constexpr (N == 64) {
                     const int grid = std::min(p->sm_count, (N + 3) * items);
                     k_plane_gain_ws<N><<<grid, 384, plane_ws_smem<N>(), st>>>(
@@ -940,7 +981,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     }
     if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.gain_ctas < 0 ||
         opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 3 || opt.plane_kernel < 0 ||
-        opt.plane_kernel > 2 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
+        opt.plane_kernel > 4 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
         return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
     if (!rho || !w_r || !sx || !sy || !sz || !w_s)
@@ -1155,6 +1196,13 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     // is 15 % faster (profiles/r02_ab64_tma.log, r02_ab32_tma.log)
     p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : (N == 64 ? 3 : 2);
     p->plane_ws = (N == 64 && opt.plane_kernel != 1) ? 1 : 0;
+    // 32^3: the radix-32 kernel (fhat line in registers) is the default: 0.115 vs 0.142 ms per 752-pair
+    // launch (profiles/r02_ab32_r32b.log); at 64^3 it is opt-in (slower than the pipelined kernel)
+    p->plane_r32 = ((N == 64 || N == 32) && p->packed && opt.plane_kernel >= 3) ? opt.plane_kernel - 2
+                   : (N == 32 && p->packed && opt.plane_kernel == 0)            ? 1
+                                                                                : 0;
+    if (opt.plane_kernel >= 3 && !p->plane_r32)
+        return (delete p, fail(BFSM_ERR_UNSUPPORTED, "plane_kernel = 3 / 4 (radix-32 plane kernel) needs a 64^3 or 32^3 grid in packed mode"));
     // work units of the register-resident x stage: a quarter of a radius' directions, at most 24 pairs
     p->seg_pairs = opt.seg_pairs > 0 ? opt.seg_pairs : std::max(1, std::min(24, (n_dir + 3) / 4));
     p->n_lanes = std::min((int)bfsm_plan::MAX_LANES, opt.batch_lanes > 0 ? opt.batch_lanes : 4);
@@ -1199,6 +1247,16 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
                 h_zpm[(size_t)q * N + t] = make_double2(ez.x + ez.y, ez.x - ez.y);
             }
         if ((rc = upload(p, &p->zpm, h_zpm))) return bail(rc);
+        if (p->plane_r32) {
+            // k_plane_gain_r32 at N = 64: lane 1 of a line feeds its radix-32 with (-1)^a in[2a+1]
+            if (N == 64)
+                for (int q = 0; q < p->pairs_local; ++q)
+                    for (int t = 3; t < N; t += 4) {
+                        cplx &z = h_zpm[(size_t)q * N + t];
+                        z = make_double2(-z.x, -z.y);
+                    }
+            if ((rc = upload(p, &p->zpm_r32, h_zpm))) return bail(rc);
+        }
     }
     if ((rc = upload(p, &p->pair_r, h_pair_r))) return bail(rc);
     if ((rc = upload(p, &p->pair_w, h_pair_w))) return bail(rc);
@@ -1255,7 +1313,7 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->stage_f) cudaFree(p->stage_f);
     if (p->stage_q) cudaFree(p->stage_q);
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < bfsm_plan::HostPipe::DEPTH; ++b) {
         if (p->pipe.f[b]) cudaFree(p->pipe.f[b]);
         if (p->pipe.q[b]) cudaFree(p->pipe.q[b]);
         if (p->pipe.in_done[b]) cudaEventDestroy(p->pipe.in_done[b]);
@@ -1387,7 +1445,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->chunk_pairs = p->chunk;
     info->launches_per_cell = do_launch_count(p);
     info->scratch_bytes = p->scratch_bytes;
-    info->plane_kernel = !p->packed ? 0 : (p->N == 64 && p->plane_ws) ? 2 : 1;
+    info->plane_kernel = !p->packed ? 0 : (p->plane_r32 && !p->cluster) ? 2 + p->plane_r32 : (p->N == 64 && p->plane_ws) ? 2 : 1;
     info->pencil_kernel = !p->packed ? 0 : p->pencil_kernel;
     info->batch_lanes_used = p->lanes_used_last;
     info->gain_pipeline = p->general ? 0 : (p->fused ? 2 : (p->cluster ? 3 : 1));
@@ -1506,7 +1564,7 @@ extern "C" int bfsm_collide_host_async(bfsm_plan *p, bfsm_comm *cm, double *Q_ho
     if (!hp.h2d) {
         CUDA_TRY(cudaStreamCreateWithFlags(&hp.h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&hp.d2h, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < bfsm_plan::HostPipe::DEPTH; ++b) {
             CUDA_TRY(cudaEventCreateWithFlags(&hp.in_done[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&hp.comp_done[b], cudaEventDisableTiming));
             CUDA_TRY(cudaEventCreateWithFlags(&hp.out_done[b], cudaEventDisableTiming));
@@ -1514,23 +1572,23 @@ extern "C" int bfsm_collide_host_async(bfsm_plan *p, bfsm_comm *cm, double *Q_ho
     }
     if (hp.cells < (size_t)n_cells) {
         CUDA_TRY(cudaDeviceSynchronize());
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < bfsm_plan::HostPipe::DEPTH; ++b) {
             if (hp.f[b]) cudaFree(hp.f[b]);
             if (hp.q[b]) cudaFree(hp.q[b]);
             hp.f[b] = hp.q[b] = nullptr;
             hp.used[b] = false;
         }
         hp.cells = 0;
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < bfsm_plan::HostPipe::DEPTH; ++b) {
             CUDA_TRY(cudaMalloc((void **)&hp.f[b], bytes));
             CUDA_TRY(cudaMalloc((void **)&hp.q[b], bytes));
         }
         hp.cells = (size_t)n_cells;
     }
-    const int b = (int)(hp.submitted & 1);
+    const int b = (int)(hp.submitted % bfsm_plan::HostPipe::DEPTH);
     cudaStream_t st = (cudaStream_t)stream;
     if (hp.used[b]) {
-        // slot b was used by the step submitted two calls ago: its Q must have reached the host (that
+        // slot b was used by the step submitted DEPTH calls ago: its Q must have reached the host (that
         // also means its kernels are done with f[b] and q[b])
         CUDA_TRY(cudaEventSynchronize(hp.out_done[b]));
     }
@@ -1554,7 +1612,7 @@ extern "C" int bfsm_collide_host_flush(bfsm_plan *p)
     if (!p) return fail(BFSM_ERR_INVALID, "plan is NULL");
     GuardDevice guard(p->device);
     if (!guard.ok) return fail(BFSM_ERR_CUDA, "cudaSetDevice failed");
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < bfsm_plan::HostPipe::DEPTH; ++b)
         if (p->pipe.used[b]) CUDA_TRY(cudaEventSynchronize(p->pipe.out_done[b]));
     return BFSM_OK;
 }

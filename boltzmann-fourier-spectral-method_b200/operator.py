@@ -192,7 +192,7 @@ class BoltzmannOperatorB200:
         """Pipelined evaluation with HOST buffers (numpy arrays or CPU tensors, ideally pinned):
         enqueues H2D copy, evaluation and D2H copy of this step and returns; the copies of neighbouring
         steps overlap the kernels (bfsm_collide_host_async).  Q is valid after flush_host(), or once
-        two further steps have been submitted.  `comm`: NcclCommunicator for a sharded plan."""
+        BFSM_HOST_PIPE_DEPTH (4) further steps have been submitted.  `comm`: NcclCommunicator for a sharded plan."""
         self._require()
         torch = _torch()
         f_np = f_in.numpy() if isinstance(f_in, torch.Tensor) else np.asarray(f_in)

@@ -91,7 +91,11 @@ typedef struct {
     int seg_pairs;         /* pairs per work unit of the register-resident x stage and of the Nyquist
                               accumulate (one partial slot per unit of a radius); 0 = heuristic */
     int plane_kernel;      /* (y,z) stage (packed mode): 0 = default, 1 = k_plane_gain3 (every warp runs
-                              all three stages), 2 = k_plane_gain_ws (warp-specialised pipeline, 64^3) */
+                              all three stages), 2 = k_plane_gain_ws (warp-specialised pipeline, 64^3),
+                              3 = k_plane_gain_r32 (radix-32 register transforms, two stages and one
+                              shared-memory exchange per plane; 64^3 and 32^3), 4 = the same with each
+                              thread's entries of the fhat plane kept in tensor memory (tcgen05.st/ld)
+                              instead of registers: more warps per SM */
     int side_stream;       /* 1: Nyquist accumulate on an internal side stream (default), 0: in line */
     int batch_lanes;       /* cells kept in flight by bfsm_collide(n_cells > 1): 1..4, 0 = default (4) */
     int gain_ctas;         /* persistent CTAs of k_plane_gain3; 0 = SMs x occupancy */
@@ -134,12 +138,14 @@ int bfsm_collide_host(bfsm_plan *plan, double *Q_host, const double *f_host, int
 /*
  * Pipelined host-pointer evaluation for callers that stream many evaluations: returns as soon as step k
  * is enqueued -- H2D copy of f on a copy stream, kernels on `stream`, D2H copy of Q on a second copy
- * stream, two staging slots -- so that the copies of neighbouring steps run under the kernels.  The call
- * blocks only until the step submitted TWO calls earlier has delivered its Q; bfsm_collide_host_flush()
+ * stream, BFSM_HOST_PIPE_DEPTH staging slots -- so that the copies of neighbouring steps run under the
+ * kernels.  The call blocks only until the step submitted BFSM_HOST_PIPE_DEPTH calls earlier has delivered its Q
+ * (a caller therefore cycles through at least that many host Q buffers); bfsm_collide_host_flush()
  * waits for everything outstanding.  Host buffers should be page-locked and must stay untouched until
  * their step is complete.  With a sharded plan pass the rank's communicator (one cell per call, every
  * rank submits the same sequence); NULL otherwise.
  */
+#define BFSM_HOST_PIPE_DEPTH 4
 int bfsm_collide_host_async(bfsm_plan *plan, bfsm_comm *comm_or_null, double *Q_host, const double *f_host,
                             int n_cells, void *stream);
 int bfsm_collide_host_flush(bfsm_plan *plan);
@@ -223,7 +229,9 @@ typedef struct {
     int launches_per_cell;   /* kernel launches issued per evaluated cell */
     long long scratch_bytes; /* device memory owned by the plan */
     int plane_kernel;        /* gain plane kernel in use: 0 k_plane_gain (4-pass, unpacked mode),
-                                1 k_plane_gain3, 2 k_plane_gain_ws (warp-specialised pipeline, 64^3) */
+                                1 k_plane_gain3, 2 k_plane_gain_ws (warp-specialised pipeline, 64^3),
+                                3 k_plane_gain_r32 (radix-32, two stages), 4 the same with the fhat line
+                                in tensor memory */
     int partial_slots;       /* partial-sum slots of S_r summed per evaluation */
     int pencil_kernel;       /* x stage in use: 0 k_pencil_gain (unpacked mode), 1 k_pencil_gain_async
                                 (LDGSTS-filled ring), 2 k_pencil_gain_reg (register resident), 3

@@ -204,14 +204,16 @@ def test_deterministic_and_chunk_independent():
 @pytest.mark.parametrize("knobs", [{"plane_kernel": 1}, {"pencil_kernel": 2}, {"pencil_kernel": 2, "plane_kernel": 1},
                                    {"pencil_kernel": 1}, {"pencil_kernel": 1, "chunk_pairs": 5},
                                    {"seg_pairs": 5}, {"side_stream": 0}, {"chunk_pairs": 7},
-                                   {"chunk_pairs": 7, "pencil_kernel": 2}, {"gain_pipeline": 2},
+                                   {"chunk_pairs": 7, "pencil_kernel": 2}, {"plane_kernel": 3}, {"plane_kernel": 4},
+                                   {"plane_kernel": 4, "chunk_pairs": 5}, {"gain_pipeline": 2},
                                    {"gain_pipeline": 2, "fused_sub_pairs": 5, "fused_ring": 3}],
                          ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
 def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
     """Every selectable kernel variant of the 64^3 path (bfsm_plan_options: the warp-specialised
     pipelined plane kernel = default vs the 3-stage plane kernel, the cp.async-staged x stage =
     default vs the register-resident one, odd work-unit sizes, the Nyquist accumulate on the main
-    stream, a chunk size that is not a multiple of the pairs per radius, the fused persistent gain
+    stream, a chunk size that is not a multiple of the pairs per radius, the radix-32 two-stage plane
+    kernel with its fhat line in registers or in tensor memory, the fused persistent gain
     kernel with two ring geometries) computes the same Q: each one
     against the CPU oracle on the non-band-limited input, and against the default variant to a few
     ulps.  No variant uses atomics: repeated evaluations are bitwise identical."""
@@ -232,6 +234,26 @@ def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
     assert rel_linf(q0, ref) <= REL_LINF_TOL
     assert rel_linf(q1, ref) <= REL_LINF_TOL
     assert rel_linf(q1, q0) <= 1e-14
+
+
+@pytest.mark.parametrize("plane_kernel", [1, 3, 4])
+@pytest.mark.parametrize("n_r,n_s,chunk", [(16, 32, 0), (3, 94, 50), (2, 6, 0), (4, 12, 1)])
+def test_plane_kernels_of_the_32_cubed_path_agree(port_oracle, plane_kernel, n_r, n_s, chunk):
+    """32^3: the three-stage plane kernel (k_plane_gain3) and the radix-32 two-stage kernel
+    (k_plane_gain_r32: a warp per plane, one shared-memory exchange; fhat line in registers = 3 or in
+    tensor memory = 4) against the oracle on the non-band-limited input, bitwise repeatable, for full and
+    for ragged launches (fewer plane entries than warps; a single pair per launch)."""
+    Nv = 32
+    f = make_input("noise", Nv)
+    opts = {"plane_kernel": plane_kernel}
+    if chunk:
+        opts["chunk_pairs"] = chunk
+    op, gl, sd = make_operator(Nv, n_r, n_s, options=opts)
+    assert op.info()["plane_kernel"] == plane_kernel
+    q = _eval(op, f)
+    assert np.array_equal(q, _eval(op, f))
+    ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), f)
+    assert rel_linf(q, ref) <= REL_LINF_TOL
 
 
 @pytest.mark.parametrize("Nv,n_r,n_s", [(32, 16, 32), (64, 4, 12), (16, 8, 6)])
@@ -454,11 +476,11 @@ def test_cpp_driver_inside_the_reference_hierarchy_matches_the_fftw_backend():
 
 
 def test_pipelined_host_entry_point_matches_the_blocking_one():
-    """bfsm_collide_host_async keeps two steps in flight (copies on their own streams); every step's Q
+    """bfsm_collide_host_async keeps BFSM_HOST_PIPE_DEPTH steps in flight (copies on their own streams); every step's Q
     must equal what the blocking host entry point returns, bit for bit, including batches."""
     Nv, n_r, n_s = 16, 4, 12
     op, _, _ = make_operator(Nv, n_r, n_s)
-    steps = 5
+    steps = 11  # wraps the staging slots more than twice
     fs = [torch.from_numpy(make_input("maxmix", Nv, seed=k).reshape(-1).copy()).pin_memory() for k in range(steps)]
     qs = [torch.empty(Nv ** 3, dtype=torch.float64).pin_memory() for _ in range(steps)]
     for k in range(steps):
