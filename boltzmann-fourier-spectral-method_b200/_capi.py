@@ -21,7 +21,7 @@ EXPORTS = (
     "bfsm_collide_host", "bfsm_gain_hat", "bfsm_finish", "bfsm_plan_get_info",
     "bfsm_plan_set_chunk", "bfsm_collide_profiled", "bfsm_sync", "bfsm_device_malloc",
     "bfsm_device_free", "bfsm_copy_to_device", "bfsm_copy_to_host", "bfsm_measure_fp64_peak",
-    "bfsm_debug_plane_work", "bfsm_debug_shares_aligned", "bfsm_debug_fail_lane_alloc", "bfsm_debug_units",
+    "bfsm_debug_plane_work", "bfsm_debug_plane_work_r32", "bfsm_debug_shares_aligned", "bfsm_debug_fail_lane_alloc", "bfsm_debug_units",
     "bfsm_plan_options_init", "bfsm_plan_create_ex", "bfsm_comm_unique_id", "bfsm_comm_init_rank",
     "bfsm_comm_init_all", "bfsm_comm_adopt", "bfsm_comm_destroy", "bfsm_collide_sharded",
     "bfsm_collide_sharded_group", "bfsm_collide_partial", "bfsm_vec_axpby", "bfsm_moments",
@@ -171,6 +171,8 @@ def load():
     lib.bfsm_debug_shares_aligned.argtypes = [ctypes.c_int] * 5
     lib.bfsm_debug_plane_work.restype = ctypes.c_int
     lib.bfsm_debug_plane_work.argtypes = [ctypes.c_int] * 4 + [ip, ip, ctypes.c_int]
+    lib.bfsm_debug_plane_work_r32.restype = ctypes.c_int
+    lib.bfsm_debug_plane_work_r32.argtypes = [ctypes.c_int] * 4 + [ip, ip, ctypes.c_int]
     _lib = lib
     return lib
 

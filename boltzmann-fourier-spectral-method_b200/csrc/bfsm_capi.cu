@@ -1196,10 +1196,11 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     // is 15 % faster (profiles/r02_ab64_tma.log, r02_ab32_tma.log)
     p->pencil_kernel = opt.pencil_kernel > 0 ? opt.pencil_kernel : (N == 64 ? 3 : 2);
     p->plane_ws = (N == 64 && opt.plane_kernel != 1) ? 1 : 0;
-    // 32^3: the radix-32 kernel (fhat line in registers) is the default: 0.115 vs 0.142 ms per 752-pair
-    // launch (profiles/r02_ab32_r32b.log); at 64^3 it is opt-in (slower than the pipelined kernel)
+    // 32^3: the radix-32 kernel with the fhat line in tensor memory is the default: 0.094 ms per 752-pair
+    // launch against 0.115 (line in registers) and 0.142 (k_plane_gain3), profiles/r02_ab32_r32c.log; at
+    // 64^3 it is opt-in (3.9 ms per evaluation against 3.2 for the pipelined kernel, r02_ab64_r32c.log)
     p->plane_r32 = ((N == 64 || N == 32) && p->packed && opt.plane_kernel >= 3) ? opt.plane_kernel - 2
-                   : (N == 32 && p->packed && opt.plane_kernel == 0)            ? 1
+                   : (N == 32 && p->packed && opt.plane_kernel == 0)            ? 2
                                                                                 : 0;
     if (opt.plane_kernel >= 3 && !p->plane_r32)
         return (delete p, fail(BFSM_ERR_UNSUPPORTED, "plane_kernel = 3 / 4 (radix-32 plane kernel) needs a 64^3 or 32^3 grid in packed mode"));
@@ -1352,6 +1353,28 @@ extern "C" int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, in
     if (n == 32) return run(LaunchWalk<32>());
     if (n == 16) return run(LaunchWalk<16>());
     return -fail(BFSM_ERR_UNSUPPORTED, "bfsm_debug_plane_work: n must be 16, 32 or 64");
+}
+
+// Same for the radix-32 plane kernel (R32Walk: one contiguous range per group, the Nyquist entries on
+// their own groups).
+extern "C" int bfsm_debug_plane_work_r32(int n, int n_items, int n_groups, int group, int *planes,
+                                         int *items, int capacity)
+{
+    if (n_items <= 0 || n_groups <= 0 || group < 0 || group >= n_groups || capacity < 0 ||
+        (capacity > 0 && (!planes || !items)))
+        return -fail(BFSM_ERR_INVALID, "bfsm_debug_plane_work_r32: bad argument");
+    auto run = [&](auto walk) {
+        walk.init(n_items, 0, group, n_groups);
+        for (int k = 0; k < walk.cnt && k < capacity; ++k) {
+            planes[k] = walk.i;
+            items[k] = walk.it;
+            walk.next();
+        }
+        return walk.cnt;
+    };
+    if (n == 64) return run(R32Walk<64>());
+    if (n == 32) return run(R32Walk<32>());
+    return -fail(BFSM_ERR_UNSUPPORTED, "bfsm_debug_plane_work_r32: n must be 32 or 64");
 }
 
 extern "C" int bfsm_debug_shares_aligned(int pairs_local, int pair_lo, int n_dir, int chunk, int groups)

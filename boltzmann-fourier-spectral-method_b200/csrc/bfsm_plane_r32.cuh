@@ -28,8 +28,8 @@
 //     out[z1]      = Y0[z1] + W64^z1 Y1[z1]        W64^(16h+i) = i^h W64^i  (compile-time W64^i)
 //     out[z1 + 32] = Y0[z1] - W64^z1 Y1[z1]
 //
-// Every group walks its own share of the flat (plane, item) list (LaunchWalk: an equal share of the N
-// regular planes and of the 3 costlier Nyquist planes), groups never synchronise with each other.
+// Every group walks its own contiguous share of the flat (plane, item) list (R32Walk), groups never
+// synchronise with each other.
 #pragma once
 #include "bfsm_kernels.cuh"
 #include "bfsm_tmem.cuh"
@@ -41,6 +41,42 @@ template <int N> struct R32Geo {
     static constexpr int GT = N * N / 32;          // threads of a group: one radix-32 unit per thread and stage
     static constexpr int PITCH = N + 1;            // row pitch of the plane buffer (== 16 bytes mod 128)
     static constexpr int SMEM_CPLX = N * PITCH + 2 * 4 * N; // plane buffer + two phase-table slots
+};
+
+// Work list of one group: the flat (plane, item) list has N*n_items regular entries followed by 3*n_items
+// Nyquist-plane entries (about 1.3 x the cost each: their multiplier is computed per element).  Groups
+// [0, gA) share the regular entries and groups [gA, n_groups) the Nyquist entries, in proportion to cost,
+// every group ONE contiguous range -- with a thousand groups per launch an equal share of both classes
+// for everybody (LaunchWalk) would make every group reload two or three planes for a couple of entries.
+template <int N> struct R32Walk {
+    int i, it, n_items, cnt, pair0;
+    __host__ __device__ __forceinline__ void init(int n_items_, int pair0_, int grp, int n_groups)
+    {
+        n_items = n_items_;
+        pair0 = pair0_;
+        const long long totA = (long long)N * n_items, totB = (long long)3 * n_items;
+        int gB = (int)(((long long)n_groups * 39 + (10 * N + 39) / 2) / (10 * N + 39)); // 3 * 1.3 : N
+        if (gB < 1) gB = 1;
+        if (gB > (int)totB) gB = (int)totB;
+        long long lo, hi;
+        if (n_groups < 2 || totB == 0) { // a single group walks the whole list
+            lo = grp == 0 ? 0 : totA + totB;
+            hi = totA + totB;
+        } else {
+            if (gB > n_groups - 1) gB = n_groups - 1;
+            const int gA = n_groups - gB;
+            if (grp < gA) { lo = (totA * grp) / gA; hi = (totA * (grp + 1)) / gA; }
+            else { lo = totA + (totB * (grp - gA)) / gB; hi = totA + (totB * (grp - gA + 1)) / gB; }
+        }
+        cnt = (int)(hi - lo);
+        i = (int)(lo / n_items);
+        it = (int)(lo % n_items);
+    }
+    __host__ __device__ __forceinline__ int pair() const { return pair0 + it; }
+    __host__ __device__ __forceinline__ void next()
+    {
+        if (++it == n_items) { it = 0; ++i; }
+    }
 };
 
 template <int N, int G> constexpr size_t plane_r32_smem() { return sizeof(cplx) * (size_t)G * R32Geo<N>::SMEM_CPLX; }
@@ -94,7 +130,7 @@ k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     // rows that feed an odd-indexed input of lane 1's radix-32 along y are stored negated
     const double ysign = (X2 && (line & 3) == 3) ? -1.0 : 1.0;
 
-    LaunchWalk<N> wk;
+    R32Walk<N> wk;
     wk.init(n_items, pair0, blockIdx.x * G + g, gridDim.x * G);
     const int cnt = wk.cnt;
 
@@ -140,22 +176,23 @@ k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         }
     };
     int cur_plane = -1, slot = 0;
-    if (cnt > 0) stage_phase(wk.pair, 0);
+    if (cnt > 0) stage_phase(wk.pair(), 0);
     cp_async_commit();
     cp_async_wait<0>();
     r32_group_sync<N>(g);
 
     for (int n = 0; n < cnt; ++n) {
-        const int i = wk.i, pair = wk.pair, dst_item = wk.dst_item;
+        const int i = wk.i, pair = wk.pair(), dst_item = wk.it;
         wk.next(); // next entry: its tables go to the other slot while this one is computed
-        if (n + 1 < cnt) stage_phase(wk.pair, slot ^ 1);
-        cp_async_commit();
 
         if (i != cur_plane) {
             // new plane: coalesced copy into the (free) plane buffer, then every thread picks its line
+            // (all N*N/GT = 32 asynchronous 16-byte copies of a thread in flight at once: one round trip)
             const cplx *srcp = (i < N) ? fhat + (size_t)i * N * N : nyq + (size_t)(i - N) * N * N;
-#pragma unroll 8
-            for (int e = t; e < N * N; e += GT) buf[(e / N) * PITCH + (e % N)] = __ldg(&srcp[e]);
+#pragma unroll
+            for (int e = t; e < N * N; e += GT) cp_async16(&buf[(e / N) * PITCH + (e % N)], &srcp[e]);
+            cp_async_commit();
+            cp_async_wait<0>();
             r32_group_sync<N>(g);
             if constexpr (TM) {
 #pragma unroll
@@ -179,6 +216,8 @@ k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
             r32_group_sync<N>(g);
             cur_plane = i;
         }
+        if (n + 1 < cnt) stage_phase(wk.pair(), slot ^ 1);
+        cp_async_commit();
         const cplx *P = phs + slot * 4 * N;
 
         // ---------------- stage A: real multiplier, radix-32 along z (+ cross-lane radix-2), row store

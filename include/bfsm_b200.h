@@ -273,6 +273,10 @@ int bfsm_measure_fp64_peak(int device, double *dfma_per_second);
  * CTA's entry count (negative BFSM_ERR_* code on bad arguments). */
 int bfsm_debug_plane_work(int n, int n_items, int n_ctas, int cta, int *planes, int *items,
                           int capacity);
+/* Same for k_plane_gain_r32 (n = 32 or 64): the entries group `group` of `n_groups` walks -- one
+ * contiguous range of the flat list per group, the three Nyquist planes on their own groups. */
+int bfsm_debug_plane_work_r32(int n, int n_items, int n_groups, int group, int *planes, int *items,
+                              int capacity);
 
 /* Test aid (no device needed): 1 if, for every launch of `chunk` pairs over a shard of `pairs_local`
  * pairs starting at global pair `pair_lo`, the `groups` equal shares of the launch all start at a

@@ -125,6 +125,42 @@ def test_plane_kernel_work_split_covers_every_entry_once_and_is_balanced(n, n_it
     assert lib.bfsm_debug_plane_work(n, 0, n_ctas, 0, None, None, 0) == -capi.BFSM_ERR_INVALID
 
 
+@pytest.mark.parametrize("n,n_items,n_groups", [(32, 752, 1184), (64, 384, 296), (64, 384, 444), (32, 1, 1184),
+                                                (64, 5, 1), (32, 3, 2), (64, 192, 7), (32, 50, 1000)])
+def test_radix32_plane_kernel_work_split(n, n_items, n_groups):
+    """k_plane_gain_r32: every (plane, item) entry exactly once; one contiguous range per group; the Nyquist
+    planes are served by their own groups (no group mixes the two classes unless it is alone); shares inside
+    a class differ by at most one entry and the two classes are balanced by cost (a Nyquist entry ~1.3 x)."""
+    lib = capi.load()
+    lib.bfsm_debug_plane_work_r32.restype = ctypes.c_int
+    seen = np.zeros((n + 3, n_items), dtype=np.int32)
+    reg, nyq = [], []
+    cap = (n + 3) * n_items
+    for grp in range(n_groups):
+        planes = (ctypes.c_int * cap)()
+        items = (ctypes.c_int * cap)()
+        cnt = lib.bfsm_debug_plane_work_r32(n, n_items, n_groups, grp, planes, items, cap)
+        assert 0 <= cnt <= cap
+        pl, it = np.frombuffer(planes, dtype=np.int32)[:cnt], np.frombuffer(items, dtype=np.int32)[:cnt]
+        np.add.at(seen, (pl, it), 1)
+        flat = pl.astype(np.int64) * n_items + it
+        assert (np.diff(flat) == 1).all()
+        if n_groups > 1:
+            assert (pl < n).all() or (pl >= n).all()
+        if cnt and (pl < n).all():
+            reg.append(cnt)
+        elif cnt:
+            nyq.append(cnt)
+    assert (seen == 1).all()
+    if n_groups > 1:
+        assert nyq, "somebody must own the Nyquist planes"
+        if reg and len(reg) + len(nyq) == n_groups:  # no idle groups: both classes evenly cut
+            assert max(reg) - min(reg) <= 1 and max(nyq) - min(nyq) <= 1
+        if n * n_items >= 20 * n_groups and n_groups >= 64:
+            assert 0.7 <= (1.3 * max(nyq)) / max(reg) <= 1.4
+    assert lib.bfsm_debug_plane_work_r32(16, 4, 4, 0, None, None, 0) == -capi.BFSM_ERR_UNSUPPORTED
+
+
 def test_single_slot_condition_matches_a_brute_force_check():
     """BFSM_ALIGNED_SLOTS=1 lets all CTA rows of the pencil / Nyquist kernels share one partial-sum
     slot when every row's share of every launch starts at a radius boundary.  The host predicate is
