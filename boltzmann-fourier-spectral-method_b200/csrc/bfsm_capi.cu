@@ -654,7 +654,7 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
                 p->S, pslots, slot_stride, nullptr, nullptr, nullptr, p->tw, p->tmp,
                 units ? p->slots_of_r : nullptr, S2, nslots, p->packed ? p->slots_of_r : nullptr);
         }
-        k_pencil_accum<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
+        k_pencil_accum<N><<<TILES, AccumGeo<N>::RS * TGP, 0, st>>>(p->tmp, p->tw, p->coef, p->n_r_local, p->M, qhat_out);
     }
     CUDA_TRY(cudaGetLastError());
     return BFSM_OK;

@@ -1029,15 +1029,24 @@ k_pencil_fwd(const cplx *__restrict__ Fh, const cplx *__restrict__ twtab, double
 }
 
 // Qhat[l] = sum_r coef[r][|l|^2] * FFT_x(Ph_r)[l]      (cpp:252-273, register reduction over r)
+// A tile is only B*TZ threads wide, and the loop over the radii is a chain of small dependent steps: with
+// one group per CTA the kernel ran one or two warps per SM and was bound by instruction latency (32^3,
+// 16 radii: 21.7 us for 8 MiB).  So RS groups per CTA take the radii r = g, g+RS, ... concurrently, each
+// with its own double-buffered tile (one barrier per radius), the entries and coefficients of a group's
+// next radius are loaded while the current one is transformed, and the groups' sums are added in the
+// fixed order g = 0..RS-1 through shared memory (deterministic).
+template <int N> struct AccumGeo { static constexpr int RS = (N == 64) ? 2 : 4; };
+
 template <int N>
-__global__ void __launch_bounds__(Geo<N>::B *TZ)
+__global__ void __launch_bounds__(AccumGeo<N>::RS *Geo<N>::B *TZ)
 k_pencil_accum(const cplx *__restrict__ Ph, const cplx *__restrict__ twtab,
                const double *__restrict__ coef, int n_r_local, int M, cplx *__restrict__ Qhat)
 {
-    constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS;
+    constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS, RS = AccumGeo<N>::RS, TG = B * TZ;
     constexpr size_t N3 = (size_t)N * N * N;
-    __shared__ __align__(16) cplx sm[N * TZ];
-    const int tg = threadIdx.x;
+    static_assert(UNITS * B * TG <= 2 * N * TZ, "the reduction reuses a group's tile buffers");
+    __shared__ __align__(16) cplx sm[RS][2][N * TZ];
+    const int g = threadIdx.x / TG, tg = threadIdx.x % TG;
     const int j = blockIdx.x / (N / TZ), kg = blockIdx.x % (N / TZ);
     const size_t off = (size_t)j * N + kg * TZ;
     cplx tw[A - 1];
@@ -1047,7 +1056,7 @@ k_pencil_accum(const cplx *__restrict__ Ph, const cplx *__restrict__ twtab,
     int msq[UNITS][B];
 #pragma unroll
     for (int m = 0; m < UNITS; ++m) {
-        const int u = tg + m * B * TZ;
+        const int u = tg + m * TG;
         const int z = u % TZ, k1 = u / TZ;
         const int lj = mode_of<N>(j), lk = mode_of<N>(kg * TZ + z);
 #pragma unroll
@@ -1057,30 +1066,80 @@ k_pencil_accum(const cplx *__restrict__ Ph, const cplx *__restrict__ twtab,
             acc[m][k2] = make_double2(0.0, 0.0);
         }
     }
-    for (int r = 0; r < n_r_local; ++r) {
-        const cplx *src = Ph + (size_t)r * N3 + off;
-        x1_pass<N, -1>(sm, tw, tg, [&](int x, int z) { return src[(size_t)x * N * N + z]; });
-        __syncthreads();
+    // this thread's pass-1 entries x = B a + b (b = tg / TZ) and coefficients of one radius
+    const int zt = tg % TZ, bt = tg / TZ;
+    cplx nxt[A];
+    double cnx[UNITS][B];
+    auto fetch = [&](int r) {
+        const cplx *src = Ph + (size_t)r * N3 + off + zt;
+#pragma unroll
+        for (int a = 0; a < A; ++a) nxt[a] = __ldg(&src[(size_t)(B * a + bt) * N * N]);
+#pragma unroll
+        for (int m = 0; m < UNITS; ++m)
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) cnx[m][k2] = __ldg(&coef[(size_t)r * M + msq[m][k2]]);
+    };
+    auto sync_group = [&]() {
+        if constexpr (TG == 32) __syncwarp();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(TG) : "memory");
+    };
+    if (g < n_r_local) fetch(g);
+    int it = 0;
+    for (int r = g; r < n_r_local; r += RS, ++it) {
+        cplx cur[A];
+        double cc[UNITS][B];
+#pragma unroll
+        for (int a = 0; a < A; ++a) cur[a] = nxt[a];
+#pragma unroll
+        for (int m = 0; m < UNITS; ++m)
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) cc[m][k2] = cnx[m][k2];
+        if (r + RS < n_r_local) fetch(r + RS);
+        cplx *tile = sm[g][it & 1];
+        // x pass 1 (x1_pass with the operands already in registers)
+        Dft<A, -1>::run(cur);
+        tile[bt * TZ + zt] = cur[0];
+#pragma unroll
+        for (int k1 = 1; k1 < A; ++k1) tile[(B * k1 + bt) * TZ + zt] = cmul(cur[k1], tw[k1 - 1]);
+        sync_group(); // this tile is complete; the group's other buffer was read before this barrier
 #pragma unroll
         for (int m = 0; m < UNITS; ++m) {
             cplx v[B];
-            x2_unit<N, -1>(sm, tg, m, v);
+            x2_unit<N, -1>(tile, tg, m, v);
 #pragma unroll
             for (int k2 = 0; k2 < B; ++k2) {
-                const double c = __ldg(&coef[(size_t)r * M + msq[m][k2]]);
-                acc[m][k2].x += c * v[k2].x;
-                acc[m][k2].y += c * v[k2].y;
+                acc[m][k2].x += cc[m][k2] * v[k2].x;
+                acc[m][k2].y += cc[m][k2] * v[k2].y;
             }
         }
-        __syncthreads();
     }
+    // fixed-order sum over the groups: groups 1.. park their sums in their own tile buffers
+    __syncthreads();
+    cplx *park = &sm[g][0][0];
+    if (g > 0) {
 #pragma unroll
-    for (int m = 0; m < UNITS; ++m) {
-        const int u = tg + m * B * TZ;
-        const int z = u % TZ, k1 = u / TZ;
+        for (int m = 0; m < UNITS; ++m)
 #pragma unroll
-        for (int k2 = 0; k2 < B; ++k2)
-            Qhat[off + (size_t)(k1 + A * k2) * N * N + z] = acc[m][k2];
+            for (int k2 = 0; k2 < B; ++k2) park[(m * B + k2) * TG + tg] = acc[m][k2];
+    }
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+        for (int m = 0; m < UNITS; ++m) {
+            const int u = tg + m * TG;
+            const int z = u % TZ, k1 = u / TZ;
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) {
+                cplx t = acc[m][k2];
+#pragma unroll
+                for (int gg = 1; gg < RS; ++gg) {
+                    const cplx o = sm[gg][0][(m * B + k2) * TG + tg];
+                    t.x += o.x;
+                    t.y += o.y;
+                }
+                Qhat[off + (size_t)(k1 + A * k2) * N * N + z] = t;
+            }
+        }
     }
 }
 
