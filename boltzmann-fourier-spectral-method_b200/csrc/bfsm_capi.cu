@@ -479,7 +479,9 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
         ProfSpan ps(p, st, BFSM_KCLASS_FORWARD);
         k_plane<N, -1, PLANE_REAL><<<dim3(N, 1), N * Geo<N>::B, plane_smem<N>(), st>>>(
             f, 1, 0, nullptr, nullptr, nullptr, p->tw, p->tmp);
-        k_pencil_fwd<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, 1.0 / (double)N3, p->fhat);
+        // (packed mode: the kernel also files the three Nyquist planes of fhat into p->nyq)
+        k_pencil_fwd<N><<<TILES, TGP, 0, st>>>(p->tmp, p->tw, 1.0 / (double)N3, p->fhat,
+                                               p->packed ? p->nyq : nullptr);
     }
 
     // gain: S_r = sum_sigma w Re(g1 g2), kept as partial slots that the next stage sums in fixed order.
@@ -490,10 +492,6 @@ template <int N> int run_gain_hat(bfsm_plan *p, cplx *qhat_out, const double *f,
     const size_t slot_stride = (size_t)p->n_r_local * N3;
     double *S2 = p->S + (size_t)pslots * slot_stride; // Nyquist slots (written once per unit, never cleared)
     if (!units) CUDA_TRY(cudaMemsetAsync(p->S, 0, sizeof(double) * (size_t)pslots * slot_stride, st));
-    if (p->packed) {
-        ProfSpan ps(p, st, BFSM_KCLASS_NYQUIST);
-        k_extract_nyq<N><<<(3 * N * N + 255) / 256, 256, 0, st>>>(p->fhat, p->nyq);
-    }
     if (p->fused) {
         if constexpr (N == 64) {
             const int n_sub = fused_subs(p);
@@ -680,9 +678,9 @@ int run_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaS
 
 template <int N> int launches_per_cell(const bfsm_plan *p)
 {
-    if (p->fused) return 2 + 1 + 1 + 1 + (p->n_r_local > 0 ? 1 : 0) + 1 + 2; // fwd, nyq extract, fused, nyq accum, accum, final
+    if (p->fused) return 2 + 1 + 1 + (p->n_r_local > 0 ? 1 : 0) + 1 + 2; // fwd, fused, nyq accum, accum, final
     const int chunks = (p->pairs_local + p->chunk - 1) / p->chunk;
-    return 2 + (p->packed ? 1 + 3 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
+    return 2 + (p->packed ? 3 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
 }
 
 // ---- general path (bfsm_general.cuh) -------------------------------------------------------

@@ -1025,7 +1025,7 @@ k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stri
 template <int N>
 __global__ void __launch_bounds__(Geo<N>::B *TZ)
 k_pencil_fwd(const cplx *__restrict__ Fh, const cplx *__restrict__ twtab, double scale,
-             cplx *__restrict__ fhat)
+             cplx *__restrict__ fhat, cplx *__restrict__ nyq = nullptr)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B, UNITS = X2<N>::UNITS;
     __shared__ __align__(16) cplx sm[N * TZ];
@@ -1044,7 +1044,15 @@ k_pencil_fwd(const cplx *__restrict__ Fh, const cplx *__restrict__ twtab, double
 #pragma unroll
         for (int k2 = 0; k2 < B; ++k2) {
             const int i = k1 + A * k2;
-            fhat[off + (size_t)i * N * N + z] = make_double2(v[k2].x * scale, v[k2].y * scale);
+            const cplx o = make_double2(v[k2].x * scale, v[k2].y * scale);
+            fhat[off + (size_t)i * N * N + z] = o;
+            if (nyq) { // the three Nyquist planes of fhat (packed mode), see k_extract_nyq
+                constexpr int H = N / 2;
+                const int kk = kg * TZ + z;
+                if (i == H) nyq[(size_t)j * N + kk] = o;
+                if (j == H) nyq[(size_t)N * N + (size_t)i * N + kk] = o;
+                if (kk == H) nyq[(size_t)2 * N * N + (size_t)i * N + j] = o;
+            }
         }
     }
 }
@@ -1208,19 +1216,8 @@ k_pencil_final(const cplx *__restrict__ H, const cplx *__restrict__ twtab,
 // Nyquist-plane correction of the PACKED mode.
 // ---------------------------------------------------------------------------------------
 
-// nyq[q][a][b]: the three Nyquist planes of fhat, q = 0: fhat(H,a,b), 1: fhat(a,H,b), 2: fhat(a,b,H)
-template <int N>
-__global__ void k_extract_nyq(const cplx *__restrict__ fhat, cplx *__restrict__ nyq)
-{
-    constexpr int H = N / 2;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= 3 * N * N) return;
-    const int q = t / (N * N), a = (t / N) % N, b = t % N;
-    const size_t src = (q == 0) ? ((size_t)H * N + a) * N + b
-                     : (q == 1) ? ((size_t)a * N + H) * N + b
-                                : ((size_t)a * N + b) * N + H;
-    nyq[t] = fhat[src];
-}
+// nyq[q][a][b]: the three Nyquist planes of fhat, q = 0: fhat(H,a,b), 1: fhat(a,H,b), 2: fhat(a,b,H) --
+// filed by k_pencil_fwd as it writes fhat.
 
 // k_nyq_accum: S2[slot][r] = sum_s Re(Y_s^2) over the pairs of one work unit,
 //   Y_s = (-1)^x U_s(y,z) + (-1)^y V_s(x,z) + (-1)^z W_s(x,y)     (sqrt(w_s) already folded into U,V,W).
