@@ -489,6 +489,8 @@ def run_b200(args):
         if batch:
             config.update({"input": "maxmix(seed=1234+c), 8 distinct cells tiled", "cells_per_step": cells_total,
                            "cells_per_rank": n_local, "parallelism": f"cell-shard x{world}",
+                           "cells_per_launch": op.info()["batch_group_cells"],
+                           "groups_or_lanes_in_flight": op.info()["batch_lanes_used"],
                            "l2_flush": "256 MiB written between steps (untimed); each step streams >> L2"})
         else:
             config.update({"input": "maxmix(seed=1234)",

@@ -40,6 +40,7 @@ class PlanInfo(ctypes.Structure):
         ("partial_slots", ctypes.c_int), ("pencil_kernel", ctypes.c_int),
         ("batch_lanes_used", ctypes.c_int), ("gain_pipeline", ctypes.c_int),
         ("ny", ctypes.c_int), ("nz", ctypes.c_int), ("general", ctypes.c_int),
+        ("batch_group_cells", ctypes.c_int),
     ]
 
 

@@ -154,6 +154,23 @@ struct bfsm_plan {
     };
     static constexpr int MAX_LANES = 4;
     Lane lanes[MAX_LANES];
+    // Batch mode, cell groups (32^3-class grids with the radix-32 plane kernel and the register x stage):
+    // every kernel of the path takes a cell dimension, so ONE launch serves up to `cells` cells -- the
+    // launch ramps, kernel tails and the latency-bound single-shot kernels are paid once per group
+    // instead of once per cell.  Two groups alternate (own scratch and streams) so that one group's
+    // tail overlaps the other group's head.
+    struct Group {
+        cplx *fhat = nullptr, *nyq = nullptr, *tmp = nullptr, *qhat = nullptr, *hyb = nullptr, *uvw = nullptr;
+        double *S = nullptr;
+        cudaStream_t main = nullptr, side = nullptr;
+        cudaEvent_t ev_plane[2] = {nullptr, nullptr}, ev_nyq[2] = {nullptr, nullptr}, done = nullptr;
+        int cells = 0;       // capacity in cells
+        int slots = 0;       // partial slots per cell S was sized for
+        bool allocated = false;
+    };
+    static constexpr int MAX_GROUPS = 2, GROUP_CELLS = 8;
+    Group groups[MAX_GROUPS];
+    int group_cells_last = 0; // cells per launch the last batch call used (0 = lane path)
     cudaEvent_t ev_fork = nullptr;
     int n_lanes = 4; // cells kept in flight in batch mode (1 = strictly sequential)
     int lane_fail_from = 0; // test hook: allocation of lanes >= this index fails (0 = off)
@@ -683,6 +700,155 @@ template <int N> int launches_per_cell(const bfsm_plan *p)
     return 2 + (p->packed ? 3 * chunks : 2 * chunks) + (p->n_r_local > 0 ? 1 : 0) + 1 + 2;
 }
 
+// ---- batch mode: groups of cells per launch ------------------------------------------------------
+bool group_path_ok(const bfsm_plan *p)
+{
+    return !p->general && p->packed && p->plane_r32 && !p->fused && !p->cluster && p->pencil_kernel == 2 &&
+           p->N == 32 && p->shard_count == 1 && p->pairs_local > 0;
+}
+void group_free(bfsm_plan *p, int k)
+{
+    bfsm_plan::Group &G = p->groups[k];
+    void *bufs[] = {G.fhat, G.nyq, G.tmp, G.qhat, G.hyb, G.uvw, G.S};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (G.main) cudaStreamDestroy(G.main);
+    if (G.side) cudaStreamDestroy(G.side);
+    for (int j = 0; j < 2; ++j) {
+        if (G.ev_plane[j]) cudaEventDestroy(G.ev_plane[j]);
+        if (G.ev_nyq[j]) cudaEventDestroy(G.ev_nyq[j]);
+    }
+    if (G.done) cudaEventDestroy(G.done);
+    G = bfsm_plan::Group();
+}
+void groups_free(bfsm_plan *p)
+{
+    for (int k = 0; k < bfsm_plan::MAX_GROUPS; ++k) group_free(p, k);
+}
+// scratch of group k for `cells` cells per launch; BFSM_ERR_NOMEM leaves the group unallocated
+int group_alloc(bfsm_plan *p, int k, int cells)
+{
+    bfsm_plan::Group &G = p->groups[k];
+    const int slots = std::max(1, pencil_slots(p) + nyq_slots(p));
+    if (G.allocated && G.cells >= cells && G.slots >= slots) return BFSM_OK;
+    group_free(p, k);
+    const size_t N = (size_t)p->N, N3 = N * N * N, C = (size_t)cells;
+    const size_t nr = (size_t)std::max(1, p->n_r_local);
+    auto need = [&](void **q, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(q, bytes ? bytes : 16);
+        if (e != cudaSuccess) {
+            *q = nullptr;
+            cudaGetLastError();
+            return fail(e == cudaErrorMemoryAllocation ? BFSM_ERR_NOMEM : BFSM_ERR_CUDA,
+                        "cudaMalloc for a batch cell group failed");
+        }
+        return BFSM_OK;
+    };
+    int rc = BFSM_OK;
+    if ((rc = need((void **)&G.fhat, sizeof(cplx) * N3 * C)) || (rc = need((void **)&G.qhat, sizeof(cplx) * N3 * C)) ||
+        (rc = need((void **)&G.nyq, sizeof(cplx) * 3 * N * N * C)) ||
+        (rc = need((void **)&G.tmp, sizeof(cplx) * N3 * std::max<size_t>(2, nr) * C)) ||
+        (rc = need((void **)&G.hyb, sizeof(cplx) * N3 * (size_t)p->chunk * C)) ||
+        (rc = need((void **)&G.uvw, sizeof(cplx) * 3 * N * N * 2 * (size_t)p->chunk * C)) ||
+        (rc = need((void **)&G.S, sizeof(double) * N3 * (size_t)slots * nr * C))) {
+        std::string keep = g_err;
+        group_free(p, k);
+        g_err = keep;
+        return rc;
+    }
+    bool ok = cudaStreamCreateWithFlags(&G.main, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&G.side, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&G.done, cudaEventDisableTiming) == cudaSuccess;
+    for (int j = 0; j < 2 && ok; ++j)
+        ok = cudaEventCreateWithFlags(&G.ev_plane[j], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&G.ev_nyq[j], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        group_free(p, k);
+        return fail(BFSM_ERR_CUDA, "stream / event creation for a batch cell group failed");
+    }
+    G.cells = cells;
+    G.slots = slots;
+    G.allocated = true;
+    return BFSM_OK;
+}
+
+// One evaluation of `cg` consecutive cells (f, Q: cg x N^3) with every kernel launched once per group
+// (run_gain_hat + run_finish with a cell dimension; the per-cell arithmetic and summation order are
+// those of the single-cell path, so the results are bitwise the same).
+template <int N> int run_group(bfsm_plan *p, bfsm_plan::Group &G, double *Q, const double *f, int cg)
+{
+    if constexpr (N != 32) {
+        return fail(BFSM_ERR_UNSUPPORTED, "cell groups are built for 32^3 grids");
+    } else {
+        constexpr size_t N3 = (size_t)N * N * N;
+        constexpr int TILES = N * N / TZ;
+        constexpr int TGP = Geo<N>::B * TZ;
+        cudaStream_t st = G.main;
+        const int nr = p->n_r_local;
+        // forward transforms (cpp:168-186)
+        k_plane<N, -1, PLANE_REAL><<<dim3(N, 1, cg), N * Geo<N>::B, plane_smem<N>(), st>>>(
+            f, 1, 0, nullptr, nullptr, nullptr, p->tw, G.tmp, nullptr, nullptr, 0, nullptr, N3, N3);
+        k_pencil_fwd<N><<<dim3(TILES, cg), TGP, 0, st>>>(G.tmp, p->tw, 1.0 / (double)N3, G.fhat, G.nyq);
+
+        const int pslots = pencil_slots(p), nslots = nyq_slots(p);
+        const size_t slot_stride = (size_t)nr * N3;
+        const size_t S_cell_stride = (size_t)(pslots + nslots) * slot_stride;
+        double *S2 = G.S + (size_t)pslots * slot_stride;
+        int ci = 0;
+        bool nyq_pending[2] = {false, false};
+        for (int c0 = 0; c0 < p->pairs_local; c0 += p->chunk, ++ci) {
+            const int nc = std::min(p->chunk, p->pairs_local - c0);
+            const int items = cg * nc;
+            const int ub = ci & 1;
+            cplx *uvw = G.uvw + (size_t)ub * 3 * N * N * p->chunk * G.cells;
+            if (nyq_pending[ub]) {
+                CUDA_TRY(cudaStreamWaitEvent(st, G.ev_nyq[ub], 0));
+                nyq_pending[ub] = false;
+            }
+            auto launch = [&](auto tm) {
+                constexpr bool TM = decltype(tm)::value;
+                using Rl = R32Launch<N, TM>;
+                const int groups = (N + 3) * items;
+                const int grid = std::max(1, std::min(p->sm_count * Rl::MINB, (groups + Rl::G - 1) / Rl::G));
+                k_plane_gain_r32<N, Rl::G, Rl::MINB, TM>
+                    <<<grid, Rl::G * R32Geo<N>::GT, plane_r32_smem<N, Rl::G>(), st>>>(
+                        G.fhat, p->phase, p->zpm_r32, G.hyb, c0, items, G.nyq, p->pair_w, uvw, nc);
+            };
+            if (p->plane_r32 == 2) launch(std::true_type{});
+            else launch(std::false_type{});
+            const int u0 = p->chunk_unit_first[ci], nu = p->chunk_unit_first[ci + 1] - u0;
+            CUDA_TRY(cudaEventRecord(G.ev_plane[ub], st));
+            CUDA_TRY(cudaStreamWaitEvent(G.side, G.ev_plane[ub], 0));
+            constexpr int NYQ_TILES = (N / 16) * (N / 16) * (N / 16);
+            k_nyq_accum<N><<<dim3(NYQ_TILES, nu, cg), 256, 0, G.side>>>(uvw, c0, p->units + u0, S2, nr, nc,
+                                                                        S_cell_stride);
+            CUDA_TRY(cudaEventRecord(G.ev_nyq[ub], G.side));
+            nyq_pending[ub] = true;
+            const dim3 grid(PencilGeo<N>::WT / PR_WARPS, nu, cg);
+            if (p->uniform_w)
+                k_pencil_gain_reg<N, true, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
+                    G.hyb, c0, p->units + u0, p->pair_w, G.S, nr, nc, S_cell_stride);
+            else
+                k_pencil_gain_reg<N, false, PR_WARPS, PR_MINB><<<grid, PR_WARPS * 32, 0, st>>>(
+                    G.hyb, c0, p->units + u0, p->pair_w, G.S, nr, nc, S_cell_stride);
+        }
+        for (int ub = 0; ub < 2; ++ub)
+            if (nyq_pending[ub]) CUDA_TRY(cudaStreamWaitEvent(st, G.ev_nyq[ub], 0));
+        // Qhat = sum_r coef_r FFT3(S_r)   (cpp:249-273)
+        if (nr > 0)
+            k_plane<N, -1, PLANE_REAL><<<dim3(N, nr, cg), N * Geo<N>::B, plane_smem<N>(), st>>>(
+                G.S, pslots, slot_stride, nullptr, nullptr, nullptr, p->tw, G.tmp, p->slots_of_r, S2, nslots,
+                p->slots_of_r, S_cell_stride, (size_t)nr * N3);
+        k_pencil_accum<N><<<dim3(TILES, cg), AccumGeo<N>::RS * TGP, 0, st>>>(G.tmp, p->tw, p->coef, nr, p->M, G.qhat);
+        // loss term, inverse transforms, combine (cpp:281-330)
+        k_plane<N, +1, PLANE_FINAL><<<dim3(N, 2, cg), N * Geo<N>::B, plane_smem<N>(), st>>>(
+            nullptr, 0, 0, G.qhat, G.fhat, p->beta2, p->tw, G.tmp, nullptr, nullptr, 0, nullptr, 0, 2 * N3);
+        k_pencil_final<N, true><<<dim3(TILES, cg), TGP, 0, st>>>(G.tmp, p->tw, f, Q);
+        CUDA_TRY(cudaGetLastError());
+        return BFSM_OK;
+    }
+}
+
 // ---- general path (bfsm_general.cuh) -------------------------------------------------------
 int gen_blocks(size_t n) { return (int)std::min<size_t>((n + 255) / 256, 148 * 16); }
 
@@ -761,6 +927,10 @@ int do_finish(bfsm_plan *p, double *Q, const cplx *qhat, const double *f, cudaSt
 {
     if (p->general) return gen_finish(p, Q, qhat, f, st, with_loss);
     DISPATCH_N(p, run_finish<N_>(p, Q, qhat, f, st, with_loss));
+}
+int do_group(bfsm_plan *p, bfsm_plan::Group &G, double *Q, const double *f, int cg)
+{
+    DISPATCH_N(p, run_group<N_>(p, G, Q, f, cg));
 }
 int do_configure(bfsm_plan *p) { DISPATCH_N(p, configure_kernels<N_>()); }
 int do_launch_count(const bfsm_plan *p)
@@ -849,8 +1019,8 @@ int lane_alloc(bfsm_plan *p, int k);
 int lanes_prepare(bfsm_plan *p, int want, int *usable)
 {
     *usable = 1;
-    if (!p->ev_fork) {
-        CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    if (!p->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    if (!p->lanes[0].main) {
         for (int k = 0; k < bfsm_plan::MAX_LANES; ++k) {
             CUDA_TRY(cudaStreamCreateWithFlags(&p->lanes[k].main, cudaStreamNonBlocking));
             CUDA_TRY(cudaEventCreateWithFlags(&p->lanes[k].done, cudaEventDisableTiming));
@@ -1305,6 +1475,7 @@ extern "C" int bfsm_plan_destroy(bfsm_plan *p)
     }
     if (p->side) cudaStreamDestroy(p->side);
     lanes_free(p);
+    groups_free(p);
     for (int k = 0; k < bfsm_plan::MAX_LANES; ++k) {
         if (p->lanes[k].main) cudaStreamDestroy(p->lanes[k].main);
         if (p->lanes[k].done) cudaEventDestroy(p->lanes[k].done);
@@ -1426,6 +1597,7 @@ extern "C" int bfsm_plan_set_chunk(bfsm_plan *p, int chunk_pairs)
     }
     CUDA_TRY(cudaDeviceSynchronize());
     lanes_free(p); // re-allocated lazily with the new chunk size
+    groups_free(p);
     if (c > p->chunk_capacity) {
         // grow the per-chunk scratch (never shrunk: the capacity, not the current chunk, is tracked)
         auto regrow = [&](void **slot, size_t bytes_new, size_t bytes_old) -> int {
@@ -1473,6 +1645,7 @@ extern "C" int bfsm_plan_get_info(const bfsm_plan *p, bfsm_plan_info *info)
     info->ny = p->ny;
     info->nz = p->nz;
     info->general = p->general;
+    info->batch_group_cells = p->group_cells_last;
     if (p->general) info->plane_kernel = info->pencil_kernel = -1;
     info->partial_slots = pencil_slots(p) + nyq_slots(p);
     return BFSM_OK;
@@ -1508,6 +1681,37 @@ extern "C" int bfsm_collide(bfsm_plan *p, double *Q_dev, const double *f_dev, in
     const size_t N3 = grid_points(p);
     cudaStream_t st = (cudaStream_t)stream;
     p->lanes_used_last = 1;
+    p->group_cells_last = 0;
+    if (n_cells >= 2 && p->n_lanes >= 2 && !p->profiling && group_path_ok(p) && p->lane_fail_from <= 0) {
+        // cell groups: up to GROUP_CELLS cells per launch, two groups in flight
+        const int cg_max = std::min((int)bfsm_plan::GROUP_CELLS, n_cells);
+        const int n_groups = (n_cells > cg_max) ? bfsm_plan::MAX_GROUPS : 1;
+        int usable = 0;
+        for (int k = 0; k < n_groups; ++k) {
+            int rc = group_alloc(p, k, cg_max);
+            if (rc == BFSM_ERR_NOMEM) break; // run with the groups that exist (or fall back to the lanes)
+            if (rc) return rc;
+            usable = k + 1;
+        }
+        if (usable > 0) {
+            if (!p->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(p->ev_fork, st));
+            for (int k = 0; k < usable; ++k) CUDA_TRY(cudaStreamWaitEvent(p->groups[k].main, p->ev_fork, 0));
+            int gi = 0;
+            for (int c = 0; c < n_cells; c += cg_max, ++gi) {
+                const int cg = std::min(cg_max, n_cells - c);
+                int rc = do_group(p, p->groups[gi % usable], Q_dev + (size_t)c * N3, f_dev + (size_t)c * N3, cg);
+                if (rc) return rc;
+            }
+            for (int k = 0; k < usable; ++k) {
+                CUDA_TRY(cudaEventRecord(p->groups[k].done, p->groups[k].main));
+                CUDA_TRY(cudaStreamWaitEvent(st, p->groups[k].done, 0));
+            }
+            p->group_cells_last = cg_max;
+            p->lanes_used_last = usable;
+            return BFSM_OK;
+        }
+    }
     if (n_cells >= 2 && p->n_lanes >= 2 && !p->profiling) {
         // only as many lanes as there are cells, and only those that could be allocated
         int nl = 1;

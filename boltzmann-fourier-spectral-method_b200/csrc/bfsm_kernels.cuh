@@ -936,7 +936,7 @@ k_pencil_gain_async(const cplx *__restrict__ hyb, const cplx *__restrict__ twtab
 }
 
 // ---------------------------------------------------------------------------------------
-// Generic single-shot plane kernel: grid (N planes, n_items), block TG = N*B.
+// Generic single-shot plane kernel: grid (N planes, n_items[, cells]), block TG = N*B.
 //   PLANE_REAL : in = sum_{g<n_partials} src_real[g*partial_stride + item*N^3 + ...] (imag 0)
 //   PLANE_FINAL: item 0: in = Qhat;  item 1: in = beta2[|l|^2] * fhat   (cpp:281-299)
 // out: dst[item][plane][y][z] in natural order.
@@ -949,13 +949,24 @@ k_plane(const double *__restrict__ src_real, int n_partials, size_t partial_stri
         const cplx *__restrict__ qhat, const cplx *__restrict__ fhat,
         const double *__restrict__ beta2, const cplx *__restrict__ twtab, cplx *__restrict__ dst,
         const int *__restrict__ n_partials_item = nullptr, const double *__restrict__ src_real2 = nullptr,
-        int n_partials2 = 0, const int *__restrict__ n_partials2_item = nullptr)
+        int n_partials2 = 0, const int *__restrict__ n_partials2_item = nullptr,
+        size_t src_cell_stride = 0, size_t dst_cell_stride = 0)
 {
     constexpr int A = Geo<N>::A, B = Geo<N>::B, TG = N * B;
     constexpr size_t N3 = (size_t)N * N * N;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx *buf = reinterpret_cast<cplx *>(smem_raw);
     const int i = blockIdx.x, item = blockIdx.y, tg = threadIdx.x;
+    // batch of cells (grid.z): every cell has its own source, spectrum and destination
+    const size_t cell = blockIdx.z;
+    if (MODE == PLANE_REAL) {
+        src_real += cell * src_cell_stride;
+        if (src_real2) src_real2 += cell * src_cell_stride;
+    } else {
+        qhat += cell * N3;
+        fhat += cell * N3;
+    }
+    dst += cell * dst_cell_stride;
 
     cplx tw[A - 1];
     load_twiddles<N, SIGN>(tw, twtab, tg % B);
@@ -1032,6 +1043,10 @@ k_pencil_fwd(const cplx *__restrict__ Fh, const cplx *__restrict__ twtab, double
     const int tg = threadIdx.x;
     const int j = blockIdx.x / (N / TZ), kg = blockIdx.x % (N / TZ);
     const size_t off = (size_t)j * N + kg * TZ;
+    // batch of cells (grid.y)
+    Fh += (size_t)blockIdx.y * N * N * N;
+    fhat += (size_t)blockIdx.y * N * N * N;
+    if (nyq) nyq += (size_t)blockIdx.y * 3 * N * N;
     cplx tw[A - 1];
     load_twiddles<N, -1>(tw, twtab, tg / TZ);
     x1_pass<N, -1>(sm, tw, tg, [&](int x, int z) { return Fh[off + (size_t)x * N * N + z]; });
@@ -1078,6 +1093,9 @@ k_pencil_accum(const cplx *__restrict__ Ph, const cplx *__restrict__ twtab,
     const int g = threadIdx.x / TG, tg = threadIdx.x % TG;
     const int j = blockIdx.x / (N / TZ), kg = blockIdx.x % (N / TZ);
     const size_t off = (size_t)j * N + kg * TZ;
+    // batch of cells (grid.y): cell c reads Ph[c][r], writes Qhat[c]
+    Ph += (size_t)blockIdx.y * n_r_local * N3;
+    Qhat += (size_t)blockIdx.y * N3;
     cplx tw[A - 1];
     load_twiddles<N, -1>(tw, twtab, tg / TZ);
 
@@ -1186,6 +1204,10 @@ k_pencil_final(const cplx *__restrict__ H, const cplx *__restrict__ twtab,
     const int tg = threadIdx.x;
     const int y = blockIdx.x / (N / TZ), zg = blockIdx.x % (N / TZ);
     const size_t off = (size_t)y * N + zg * TZ;
+    // batch of cells (grid.y): cell c reads H[c][0..1], f[c], writes Q[c]
+    H += (size_t)blockIdx.y * (WITH_LOSS ? 2 : 1) * N3;
+    f += (size_t)blockIdx.y * N3;
+    Q += (size_t)blockIdx.y * N3;
     cplx tw[A - 1];
     load_twiddles<N, +1>(tw, twtab, tg / TZ);
     x1_pass<N, +1>(sm[0], tw, tg, [&](int x, int z) { return H[off + (size_t)x * N * N + z]; });
@@ -1231,8 +1253,11 @@ k_pencil_final(const cplx *__restrict__ H, const cplx *__restrict__ twtab,
 template <int N>
 __global__ void __launch_bounds__(256, 2)
 k_nyq_accum(const cplx *__restrict__ uvw, int uvw_pair0, const PencilUnit *__restrict__ units,
-            double *__restrict__ S2, int n_r_local)
+            double *__restrict__ S2, int n_r_local, int pairs_per_cell = 0, size_t S_cell_stride = 0)
 {
+    // batch of cells (grid.z): cell c's fields of the launch follow those of cell c-1
+    uvw += (size_t)blockIdx.z * pairs_per_cell * 3 * N * N;
+    S2 += (size_t)blockIdx.z * S_cell_stride;
     constexpr int NT = 16, TPD = N / NT, PADR = NT + 2, STAGES = 3;
     constexpr size_t N3 = (size_t)N * N * N;
     __shared__ __align__(16) cplx ring[STAGES][3][NT][PADR]; // [stage][U|V|W][row][col]

@@ -182,13 +182,17 @@ template <int N> struct PencilLane {
     }
 };
 
-// grid (WT / WARPS warp-tile groups, n_units), block WARPS*32.
+// grid (WT / WARPS warp-tile groups, n_units[, cells]), block WARPS*32.
 template <int N, bool UNIFORM_W, int WARPS, int MINB>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 k_pencil_gain_reg(const cplx *__restrict__ hyb, int hyb_pair0, const PencilUnit *__restrict__ units,
-                  const double *__restrict__ pair_w, double *__restrict__ S, int n_r_local)
+                  const double *__restrict__ pair_w, double *__restrict__ S, int n_r_local,
+                  int pairs_per_cell = 0, size_t S_cell_stride = 0)
 {
     constexpr size_t N2 = (size_t)N * N, N3 = N2 * N;
+    // batch of cells (grid.z): cell c's hybrid grids of the launch follow those of cell c-1
+    hyb += (size_t)blockIdx.z * pairs_per_cell * N3;
+    S += (size_t)blockIdx.z * S_cell_stride;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     PencilLane<N> L;
     L.init(lane, blockIdx.x * WARPS + warp);

@@ -113,8 +113,12 @@ __global__ void __launch_bounds__(G * R32Geo<N>::GT, MINB)
 k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                  const cplx *__restrict__ zpm, cplx *__restrict__ hyb, int pair0, int n_items,
                  const cplx *__restrict__ nyq, const double *__restrict__ pair_w,
-                 cplx *__restrict__ uvw)
+                 cplx *__restrict__ uvw, int pairs_per_cell = 0)
 {
+    // Batch of cells: the launch's n_items = cells x pairs_per_cell; item `it` belongs to cell it / pairs_per_cell
+    // (own fhat and Nyquist planes) and to pair pair0 + it % pairs_per_cell (phase tables, weight); the
+    // hybrid grids and Nyquist fields of the launch are stored by item index.  pairs_per_cell = 0: one cell.
+    const int ppc = pairs_per_cell > 0 ? pairs_per_cell : n_items;
     constexpr int GT = R32Geo<N>::GT, PITCH = R32Geo<N>::PITCH, H = N / 2;
     constexpr bool X2 = (N == 64); // two lanes share a line
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -176,19 +180,21 @@ k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
         }
     };
     int cur_plane = -1, slot = 0;
-    if (cnt > 0) stage_phase(wk.pair(), 0);
+    if (cnt > 0) stage_phase(pair0 + wk.it % ppc, 0);
     cp_async_commit();
     cp_async_wait<0>();
     r32_group_sync<N>(g);
 
     for (int n = 0; n < cnt; ++n) {
-        const int i = wk.i, pair = wk.pair(), dst_item = wk.it;
+        const int i = wk.i, dst_item = wk.it, cell = wk.it / ppc, pair = pair0 + wk.it % ppc;
+        const int plane_key = cell * (N + 3) + i;
         wk.next(); // next entry: its tables go to the other slot while this one is computed
 
-        if (i != cur_plane) {
+        if (plane_key != cur_plane) {
             // new plane: coalesced copy into the (free) plane buffer, then every thread picks its line
             // (all N*N/GT = 32 asynchronous 16-byte copies of a thread in flight at once: one round trip)
-            const cplx *srcp = (i < N) ? fhat + (size_t)i * N * N : nyq + (size_t)(i - N) * N * N;
+            const cplx *srcp = (i < N) ? fhat + ((size_t)cell * N + i) * N * N
+                                       : nyq + ((size_t)cell * 3 + (i - N)) * N * N;
 #pragma unroll
             for (int e = t; e < N * N; e += GT) cp_async16(&buf[(e / N) * PITCH + (e % N)], &srcp[e]);
             cp_async_commit();
@@ -214,9 +220,9 @@ k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
                 for (int a = 0; a < 32; ++a) fr[a] = buf[line * PITCH + (X2 ? 2 * a + hb : a)];
             }
             r32_group_sync<N>(g);
-            cur_plane = i;
+            cur_plane = plane_key;
         }
-        if (n + 1 < cnt) stage_phase(wk.pair(), slot ^ 1);
+        if (n + 1 < cnt) stage_phase(pair0 + wk.it % ppc, slot ^ 1);
         cp_async_commit();
         const cplx *P = phs + slot * 4 * N;
 

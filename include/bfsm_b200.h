@@ -97,7 +97,8 @@ typedef struct {
                               thread's entries of the fhat plane kept in tensor memory (tcgen05.st/ld)
                               instead of registers: more warps per SM */
     int side_stream;       /* 1: Nyquist accumulate on an internal side stream (default), 0: in line */
-    int batch_lanes;       /* cells kept in flight by bfsm_collide(n_cells > 1): 1..4, 0 = default (4) */
+    int batch_lanes;       /* cells kept in flight by bfsm_collide(n_cells > 1): 1..4, 0 = default (4); 1 also
+                              switches the cell-group path of the 32^3 grids off */
     int gain_ctas;         /* persistent CTAs of k_plane_gain3; 0 = SMs x occupancy */
     int gain_pipeline;     /* 0 = default, 1 = one plane + one x kernel per chunk (hybrid grids through
                               HBM), 2 = fused persistent kernel (64^3 packed mode only): plane, Nyquist and
@@ -241,6 +242,9 @@ typedef struct {
                                 0 = general-grid path */
     int ny, nz;              /* points along y and z (`n` is the x size) */
     int general;             /* 1 if the general-grid path (bfsm_general.cuh) serves this plan */
+    int batch_group_cells;   /* cells per kernel launch the last bfsm_collide(n_cells > 1) used: > 0 = the
+                                cell-group path (32^3: every kernel has a cell dimension; batch_lanes_used
+                                then counts the groups in flight), 0 = one cell per launch on lanes */
 } bfsm_plan_info;
 
 int bfsm_plan_get_info(const bfsm_plan *plan, bfsm_plan_info *info);

@@ -311,6 +311,42 @@ def test_special_pipelines_reject_grids_they_are_not_written_for():
         assert err.value.code == capi.BFSM_ERR_UNSUPPORTED
 
 
+@pytest.mark.parametrize("plane_kernel,chunk", [(0, 0), (3, 0), (4, 5)])
+def test_cell_groups_of_the_32_cubed_batch_path_match_cell_by_cell(port_oracle, plane_kernel, chunk):
+    """32^3 batches run in CELL GROUPS: every kernel of the path takes a cell dimension and one launch
+    serves up to eight cells (two groups in flight).  Eleven cells = one full group + a ragged one; every
+    cell's Q must equal the single-cell evaluation BIT FOR BIT (same per-cell arithmetic and summation
+    order), for one launch per cell group and for several chunks per group, and agree with the oracle."""
+    Nv, n_r, n_s, cells = 32, 3, 12, 11
+    opts = {"plane_kernel": plane_kernel}
+    if chunk:
+        opts["chunk_pairs"] = chunk
+    op, gl, sd = make_operator(Nv, n_r, n_s, options=opts)
+    fs = np.stack([make_input("noise" if c % 2 else "maxmix", Nv, seed=c) for c in range(cells)])
+    f_dev = torch.from_numpy(fs).cuda().reshape(-1)
+    Q_dev = torch.empty_like(f_dev)
+    op(Q_dev, f_dev, n_cells=cells)
+    torch.cuda.synchronize()
+    info = op.info()
+    assert info["batch_group_cells"] == 8 and info["batch_lanes_used"] == 2
+    Q = Q_dev.cpu().numpy().reshape(cells, -1)
+    for c in range(cells):
+        assert np.array_equal(_eval(op, fs[c]).ravel(), Q[c]), c
+    for c in (0, 7, 8, cells - 1):
+        ref = port_oracle.collide((Nv,) * 3, *oracle_args(gl, sd), fs[c])
+        assert rel_linf(Q[c].reshape(Nv, Nv, Nv), ref) <= REL_LINF_TOL
+    # a batch that fits one group; then lanes only (batch_lanes = 1 switches the groups off)
+    op(Q_dev, f_dev, n_cells=3)
+    torch.cuda.synchronize()
+    assert op.info()["batch_group_cells"] == 3 and op.info()["batch_lanes_used"] == 1
+    assert np.array_equal(Q_dev.cpu().numpy().reshape(cells, -1)[:3], Q[:3])
+    # in place (Q aliases f), like the single-cell entry point allows
+    buf = f_dev.clone()
+    op(buf, buf, n_cells=cells)
+    torch.cuda.synchronize()
+    assert np.array_equal(buf.cpu().numpy().reshape(cells, -1), Q)
+
+
 def test_batch_runs_with_fewer_lanes_when_lane_memory_is_short():
     """bfsm_collide(n_cells > 1) keeps up to four cells in flight on lanes with their own scratch; when
     a lane cannot be allocated (BFSM_ERR_NOMEM, injected here) the batch runs on the lanes that exist
