@@ -507,7 +507,10 @@ def run_b200(args):
                     "d2h_bytes_per_step": 8 * N3 * n_local,
                     "how": "op.submit_host per step (pinned host buffers, H2D + kernels + D2H, four steps in "
                            "flight), flush at the end; wall clock, max over ranks"},
-            "gpu_launches": info["launches_per_cell"] * max(n_local, 1) * steps,
+            # (cell-group path: one launch sequence per GROUP of cells, not per cell)
+            "gpu_launches": info["launches_per_cell"] * steps * (
+                -(-max(n_local, 1) // op.info()["batch_group_cells"]) if batch and op.info()["batch_group_cells"] > 0
+                else max(n_local, 1)),
             "parity": parity, "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
         args.emit(json.dumps(line))
