@@ -53,7 +53,7 @@ class PlanOptions(ctypes.Structure):
         ("side_stream", ctypes.c_int), ("batch_lanes", ctypes.c_int), ("gain_ctas", ctypes.c_int),
         ("gain_pipeline", ctypes.c_int), ("fused_sub_pairs", ctypes.c_int), ("fused_ring", ctypes.c_int),
         ("fused_pencil_ctas", ctypes.c_int), ("fused_nyq_ctas", ctypes.c_int),
-        ("reserved", ctypes.c_int * 3),
+        ("pencil_groups", ctypes.c_int), ("reserved", ctypes.c_int * 2),
     ]
 
 
@@ -67,7 +67,7 @@ ENV_OPTIONS = {
     "BFSM_BATCH_LANES": "batch_lanes", "BFSM_GAIN_CTAS": "gain_ctas",
     "BFSM_GAIN_PIPELINE": "gain_pipeline", "BFSM_FUSED_SUB_PAIRS": "fused_sub_pairs",
     "BFSM_FUSED_RING": "fused_ring", "BFSM_FUSED_PENCIL_CTAS": "fused_pencil_ctas",
-    "BFSM_FUSED_NYQ_CTAS": "fused_nyq_ctas",
+    "BFSM_FUSED_NYQ_CTAS": "fused_nyq_ctas", "BFSM_PENCIL_GROUPS": "pencil_groups",
 }
 
 

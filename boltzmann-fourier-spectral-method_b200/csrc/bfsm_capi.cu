@@ -1149,7 +1149,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     }
     if (opt.chunk_pairs < 0 || opt.seg_pairs < 0 || opt.gain_ctas < 0 ||
         opt.batch_lanes < 0 || opt.pencil_kernel < 0 || opt.pencil_kernel > 3 || opt.plane_kernel < 0 ||
-        opt.plane_kernel > 4 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
+        opt.plane_kernel > 4 || opt.pencil_groups < 0 || opt.gain_pipeline < 0 || opt.gain_pipeline > 3)
         return fail(BFSM_ERR_INVALID, "bfsm_plan_options: field out of range");
     *out = nullptr;
     if (!rho || !w_r || !sx || !sy || !sz || !w_s)
@@ -1354,6 +1354,7 @@ extern "C" int bfsm_plan_create_ex(bfsm_plan **out, int nvx, int nvy, int nvz, i
     p->chunk = std::min(p->chunk, std::max(1, p->pairs_local));
     p->chunk_capacity = p->chunk;
     p->G = (N == 64) ? Launch<64>::G : (N == 32) ? Launch<32>::G : Launch<16>::G;
+    if (opt.pencil_groups > 0) p->G = std::min(opt.pencil_groups, 64);
     {
         const int occ = (N == 64) ? Launch<64>::MINB : (N == 32) ? Launch<32>::MINB : Launch<16>::MINB;
         p->gy = opt.gain_ctas > 0 ? opt.gain_ctas : p->sm_count * occ;

@@ -110,7 +110,10 @@ typedef struct {
     int fused_ring;        /* fused kernel: ring slots (sub-chunks in flight); 0 = default (2) */
     int fused_pencil_ctas; /* fused kernel: CTAs (= SMs) of the x role; 0 = default */
     int fused_nyq_ctas;    /* fused kernel: CTAs of the Nyquist-plane role, a multiple of 3; 0 = default */
-    int reserved[3];
+    int pencil_groups;     /* staged x stage (pencil_kernel 1 / 3): CTA rows a chunk's pairs are split over
+                              (grid = tiles x rows; one partial slot per row unless every row's share starts
+                              at a radius boundary); 0 = default */
+    int reserved[2];
 } bfsm_plan_options;
 
 void bfsm_plan_options_init(bfsm_plan_options *opts);

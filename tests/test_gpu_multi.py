@@ -44,8 +44,17 @@ errc = float((Qc - Q_full).abs().max() / Q_full.abs().max())
 gathered = [torch.empty_like(Qc) for _ in range(world)]
 dist.all_gather(gathered, Qc)
 samec = all(torch.equal(g, gathered[0]) for g in gathered)
+# (c) streamed host buffers through the sharded plan (bfsm_collide_host_async with the communicator, four
+# steps in flight): each step's Q must equal (b) bit for bit
+steps = 7
+fh = f.cpu().pin_memory()
+qh = [torch.empty(Nv ** 3, dtype=torch.float64).pin_memory() for _ in range(steps)]
+for k in range(steps):
+    shard.submit_host(qh[k], fh, comm=comm)
+shard.flush_host()
+sameh = all(torch.equal(q, Qc.cpu()) for q in qh)
 if rank == 0:
-    print(f"RESULT err={err:.3e} same={same} errc={errc:.3e} samec={samec} pairs_local={shard.info()['pairs_local']}")
+    print(f"RESULT err={err:.3e} same={same} errc={errc:.3e} samec={samec} sameh={sameh} pairs_local={shard.info()['pairs_local']}")
 comm.close()
 dist.destroy_process_group()
 '''
@@ -66,7 +75,7 @@ def test_pair_sharding_over_nccl(tmp_path):
     err = float(line.split("err=")[1].split()[0])
     errc = float(line.split("errc=")[1].split()[0])
     assert err <= 1e-13 and errc <= 1e-13, line
-    assert "same=True" in line and "samec=True" in line, line
+    assert "same=True" in line and "samec=True" in line and "sameh=True" in line, line
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
