@@ -516,7 +516,7 @@ def test_pipelined_host_entry_point_matches_the_blocking_one():
     must equal what the blocking host entry point returns, bit for bit, including batches."""
     Nv, n_r, n_s = 16, 4, 12
     op, _, _ = make_operator(Nv, n_r, n_s)
-    steps = 11  # wraps the staging slots more than twice
+    steps = 19  # wraps the staging slots more than twice
     fs = [torch.from_numpy(make_input("maxmix", Nv, seed=k).reshape(-1).copy()).pin_memory() for k in range(steps)]
     qs = [torch.empty(Nv ** 3, dtype=torch.float64).pin_memory() for _ in range(steps)]
     for k in range(steps):

@@ -26,6 +26,14 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.bfsm_version() == 100
 
 
+def test_constants_mirror_the_header():
+    with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
+        header = fh.read()
+    for name in ("BFSM_HOST_PIPE_DEPTH", "BFSM_UNIQUE_ID_BYTES"):
+        value = int(re.search(r"#define\s+%s\s+(\d+)" % name, header).group(1))
+        assert getattr(capi, name) == value, name
+
+
 def test_plan_info_mirror_matches_the_header_field_by_field():
     """The ctypes mirror of bfsm_plan_info must list the header's fields in the same order with the
     same C types (the library fills the struct through a plain pointer)."""
