@@ -26,6 +26,15 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.bfsm_version() == 100
 
 
+def test_integration_notes_name_every_entry_point():
+    with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
+        declared = set(re.findall(r"\b(bfsm_[a-z_0-9]+)\s*\(", fh.read())) - {"bfsm_plan", "bfsm_plan_info"}
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as fh:
+        notes = fh.read()
+    missing = [d for d in sorted(declared) if d not in notes]
+    assert not missing, missing
+
+
 def test_constants_mirror_the_header():
     with open(os.path.join(ROOT, "include", "bfsm_b200.h")) as fh:
         header = fh.read()

@@ -3,9 +3,10 @@
 listings of the two gain kernels of the default 64^3 pipeline (encodings stripped).
 
     python tools/sass_summary.py        ->  profiles/r02_sass_summary.txt, r02_sass_k_plane_gain_ws.txt,
-                                            r02_sass_k_pencil_gain_async_tma.txt
+                                            r02_sass_k_pencil_gain_async_tma.txt, r02_sass_k_plane_gain_r32_tmem_32.txt
 
 What to look for: UTMALDG (cp.async.bulk.tensor: the TMA-filled x-stage ring) + SYNCS (mbarrier),
+LDTM / STTM / UTCATOMSWS (tcgen05.ld / .st / .alloc: the fhat line of the radix-32 plane kernel in tensor memory),
 USETMAXREG (register hand-over between the warpgroups of the pipelined plane kernel), UCGABAR_* (cluster
 barriers of the 32^3 DSMEM kernel), LDGSTS (cp.async), SHFL (lane butterflies of the register-resident
 x stage), no HMMA/DMMA (fp64 butterflies are not a contraction; DMMA shares the FP64 pipe on sm_100a,
@@ -20,8 +21,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "boltzmann-fourier-spectral-method_b200", "csrc", "libbfsm_b200.so")
 OUT = os.path.join(ROOT, "profiles")
 KEEP = {"k_plane_gain_wsILi64E": "r02_sass_k_plane_gain_ws.txt",
-        "k_pencil_gain_asyncILi64ELi4ELi3ELi2ELb0ELb1": "r02_sass_k_pencil_gain_async_tma.txt"}
-INTERESTING = ["UTMALDG", "UBLKCP", "SYNCS", "LDGSTS", "USETMAXREG", "UCGABAR_ARV", "UCGABAR_WAIT", "BAR", "DFMA",
+        "k_pencil_gain_asyncILi64ELi4ELi3ELi2ELb0ELb1": "r02_sass_k_pencil_gain_async_tma.txt",
+        "k_plane_gain_r32ILi32ELi11ELi1ELb1": "r02_sass_k_plane_gain_r32_tmem_32.txt"}
+INTERESTING = ["UTMALDG", "UBLKCP", "SYNCS", "LDTM", "STTM", "UTCATOMSWS", "LDGSTS", "USETMAXREG", "UCGABAR_ARV", "UCGABAR_WAIT", "BAR", "DFMA",
                "DADD", "DMUL", "SHFL", "LDS", "STS", "LDG", "STG", "ST", "LD", "ATOMG", "MEMBAR", "HMMA", "DMMA",
                "LDL", "STL"]
 
