@@ -205,7 +205,8 @@ def test_deterministic_and_chunk_independent():
                                    {"pencil_kernel": 1}, {"pencil_kernel": 1, "chunk_pairs": 5},
                                    {"seg_pairs": 5}, {"side_stream": 0}, {"chunk_pairs": 7},
                                    {"chunk_pairs": 7, "pencil_kernel": 2}, {"plane_kernel": 3}, {"plane_kernel": 4},
-                                   {"plane_kernel": 4, "chunk_pairs": 5}, {"gain_pipeline": 2},
+                                   {"plane_kernel": 4, "chunk_pairs": 5}, {"pencil_groups": 4},
+                                   {"pencil_groups": 3, "pencil_kernel": 1, "chunk_pairs": 7}, {"gain_pipeline": 2},
                                    {"gain_pipeline": 2, "fused_sub_pairs": 5, "fused_ring": 3}],
                          ids=lambda k: ",".join(f"{a}={b}" for a, b in k.items()))
 def test_kernel_variants_agree_with_the_oracle(port_oracle, knobs):
