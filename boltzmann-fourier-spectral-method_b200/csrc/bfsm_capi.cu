@@ -1534,7 +1534,7 @@ extern "C" int bfsm_debug_plane_work_r32(int n, int n_items, int n_groups, int g
         (capacity > 0 && (!planes || !items)))
         return -fail(BFSM_ERR_INVALID, "bfsm_debug_plane_work_r32: bad argument");
     auto run = [&](auto walk) {
-        walk.init(n_items, 0, group, n_groups);
+        walk.init(n_items, group, n_groups);
         for (int k = 0; k < walk.cnt && k < capacity; ++k) {
             planes[k] = walk.i;
             items[k] = walk.it;

@@ -49,11 +49,10 @@ template <int N> struct R32Geo {
 // every group ONE contiguous range -- with a thousand groups per launch an equal share of both classes
 // for everybody (LaunchWalk) would make every group reload two or three planes for a couple of entries.
 template <int N> struct R32Walk {
-    int i, it, n_items, cnt, pair0;
-    __host__ __device__ __forceinline__ void init(int n_items_, int pair0_, int grp, int n_groups)
+    int i, it, n_items, cnt;
+    __host__ __device__ __forceinline__ void init(int n_items_, int grp, int n_groups)
     {
         n_items = n_items_;
-        pair0 = pair0_;
         const long long totA = (long long)N * n_items, totB = (long long)3 * n_items;
         int gB = (int)(((long long)n_groups * 39 + (10 * N + 39) / 2) / (10 * N + 39)); // 3 * 1.3 : N
         if (gB < 1) gB = 1;
@@ -72,7 +71,6 @@ template <int N> struct R32Walk {
         i = (int)(lo / n_items);
         it = (int)(lo % n_items);
     }
-    __host__ __device__ __forceinline__ int pair() const { return pair0 + it; }
     __host__ __device__ __forceinline__ void next()
     {
         if (++it == n_items) { it = 0; ++i; }
@@ -135,7 +133,7 @@ k_plane_gain_r32(const cplx *__restrict__ fhat, const cplx *__restrict__ phase,
     const double ysign = (X2 && (line & 3) == 3) ? -1.0 : 1.0;
 
     R32Walk<N> wk;
-    wk.init(n_items, pair0, blockIdx.x * G + g, gridDim.x * G);
+    wk.init(n_items, blockIdx.x * G + g, gridDim.x * G);
     const int cnt = wk.cnt;
 
     auto stage_phase = [&](int pair_src, int slot_dst) {
