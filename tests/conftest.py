@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # pytest-timeout registers this itself when it is installed; harmless (and silent) otherwise
+    config.addinivalue_line("markers", "timeout(seconds): fail instead of hanging (pytest-timeout)")
 
 
 @pytest.fixture(scope="session")

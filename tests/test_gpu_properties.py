@@ -348,6 +348,28 @@ def test_cell_groups_of_the_32_cubed_batch_path_match_cell_by_cell(port_oracle, 
     assert np.array_equal(buf.cpu().numpy().reshape(cells, -1), Q)
 
 
+@pytest.mark.timeout(180)
+def test_32_cubed_batch_on_lanes_with_concurrent_tensor_memory_kernels():
+    """A 32^3 plan whose x stage is the staged kernel cannot use the cell groups: the batch runs on four
+    lanes, i.e. up to four radix-32 plane kernels -- each CTA allocating tensor memory -- are in flight on
+    different streams.  They must neither deadlock on the allocation nor disturb each other's lines: every
+    cell equals the single-cell evaluation bit for bit."""
+    Nv, n_r, n_s, cells = 32, 3, 12, 7
+    op, gl, sd = make_operator(Nv, n_r, n_s, options={"pencil_kernel": 1})
+    assert op.info()["plane_kernel"] == 4
+    fs = np.stack([make_input("maxmix", Nv, seed=c) for c in range(cells)])
+    f_dev = torch.from_numpy(fs).cuda().reshape(-1)
+    Q_dev = torch.empty_like(f_dev)
+    for _ in range(3):
+        op(Q_dev, f_dev, n_cells=cells)
+    torch.cuda.synchronize()
+    info = op.info()
+    assert info["batch_group_cells"] == 0 and info["batch_lanes_used"] == 4
+    Q = Q_dev.cpu().numpy().reshape(cells, -1)
+    for c in range(cells):
+        assert np.array_equal(_eval(op, fs[c]).ravel(), Q[c]), c
+
+
 def test_batch_runs_with_fewer_lanes_when_lane_memory_is_short():
     """bfsm_collide(n_cells > 1) keeps up to four cells in flight on lanes with their own scratch; when
     a lane cannot be allocated (BFSM_ERR_NOMEM, injected here) the batch runs on the lanes that exist
